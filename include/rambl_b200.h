@@ -1,0 +1,122 @@
+/* rambl_b200.h -- C ABI of the B200-native StrainCall hot path.
+ *
+ * Drop-in boundary for RAMBL's StrainCall (reference: homopolymer/RAMBL, StrainCall/).  Every entry
+ * point names the reference interface it replaces.  Plain pointers and sizes only; all functions
+ * return 0 (RAMBL_OK) or a positive error code, and rambl_last_error() gives the message.  There is
+ * no CPU fallback: anything that needs the device fails with RAMBL_ERR_CUDA when none is usable.
+ *
+ * A "subgroup" is one StrainCall problem: a gene window plus the reads mapped to it, in the form
+ * StrainCall holds them after load_mapping_reads (StrainCall.cpp:480-670): de-duplicated AlignRead
+ * tuples <relative_pos, cigar, seq, "", copies> and ReadPairs uid -> one mate uid (or -1) per copy.
+ * A "batch" is any number of subgroups that are built and solved together (scripts/rambl.py runs
+ * one StrainCall process per seed gene, rambl.py:165-194; here they share the device launches).
+ */
+#ifndef RAMBL_B200_H
+#define RAMBL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum
+{
+    RAMBL_OK = 0,
+    RAMBL_ERR_CUDA = 1,       /* no usable sm_100 device, or a CUDA call failed */
+    RAMBL_ERR_INVALID = 2,    /* malformed input */
+    RAMBL_ERR_CAPACITY = 3,   /* a problem exceeds a compiled-in kernel limit */
+    RAMBL_ERR_NO_STRAINS = 4, /* every candidate strain was pruned (the reference is undefined here) */
+    RAMBL_ERR_STATE = 5       /* calls made in the wrong order */
+};
+
+typedef struct rambl_batch rambl_batch;
+
+typedef struct rambl_stats
+{
+    int32_t gpu_launches;     /* kernels launched by this library since the batch was created */
+    int32_t level_steps;      /* level-synchronous steps of the strain search */
+    int64_t draws;            /* categorical draws of the Gibbs sweeps */
+    int64_t loglik_updates;   /* (read-pool entry, strain) log-likelihood updates */
+    int64_t msa_dp_cells;     /* (profile column x letter) cells of the insertion alignments */
+    int32_t msa_problems;
+    float msa_kernel_ms;      /* CUDA-event time of the alignment kernel */
+    float infer_gpu_ms;       /* CUDA-event time of rambl_batch_infer, first launch to last */
+    int64_t h2d_bytes;        /* bytes copied host->device / device->host by the library */
+    int64_t d2h_bytes;
+} rambl_stats;
+
+const char* rambl_last_error(void);
+int rambl_device_count(void);
+void rambl_free(void* p); /* for every char* this library returns */
+
+/* ---- MultipleSequenceAlignmentSP<Index2D,SimpleScoreModel,vector,string,char>::align
+ *      (MultipleSequenceAlignment.hpp:87-107, MultipleSequenceAlignmentSP.cpp:10-301), batched.
+ * Problem p aligns sequences prob_seq_off[p] .. prob_seq_off[p+1]-1 in that order; sequence s is
+ * letters[seq_off[s] .. seq_off[s+1]).  On return width[p] is the profile width (MSA::size()) and row
+ * t of problem p (MSA::get(t)) is rows[row_off[p] + t*row_stride[p] .. + width[p]).  rows must hold
+ * rambl_msa_rows_capacity() bytes. dp_cells / kernel_ms may be NULL. */
+int64_t rambl_msa_rows_capacity(int32_t n_problems, const int32_t* prob_seq_off, const int32_t* seq_off);
+int rambl_msa_sp_align_batch(int32_t n_problems, const int32_t* prob_seq_off, const int32_t* seq_off,
+                             const char* letters, int32_t* width, int64_t* row_off, int32_t* row_stride, char* rows,
+                             uint64_t* dp_cells, float* kernel_ms);
+
+/* ---- batches */
+rambl_batch* rambl_batch_create(void);
+void rambl_batch_destroy(rambl_batch* b);
+
+/* One subgroup = the arguments of PartialOrderGraph(GenomeSeq& G, vector<AlignRead>& R)
+ * (PartialOrderGraph.hpp:236) plus the ReadPairs later given to infer_strains / read_assign
+ * (PartialOrderGraph.hpp:335-340) as CSR: mates of unique read u are pair_val[pair_off[u] ..
+ * pair_off[u+1]), one per copy.  pair_off/pair_val may be NULL (no read is paired).
+ * Returns the subgroup index (>= 0) or -error. */
+int rambl_batch_add_subgroup(rambl_batch* b, const char* gene, int32_t n_reads, const int32_t* pos,
+                             const char* const* cigar, const char* const* seq, const int32_t* copies,
+                             const int32_t* pair_off, const int32_t* pair_val);
+
+/* PartialOrderGraph::build (PartialOrderGraph.cpp:67-265) for every subgroup added so far; the
+ * insertion alignments of all subgroups run in one device launch. */
+int rambl_batch_build_graphs(rambl_batch* b);
+
+/* The same construction with the device step taken out, for hosts that already hold the aligned
+ * rows: thread_reads() splices the reads and lists the alignment problems (text: one line
+ * "P <index> <n>" per problem followed by its n sequences, one per line);
+ * finish_graphs_with_rows() takes the rows in the same layout ("P <index> <n>", then n rows). */
+int rambl_batch_thread_reads(rambl_batch* b);
+char* rambl_batch_msa_problems_text(rambl_batch* b);
+int rambl_batch_finish_graphs_with_rows(rambl_batch* b, const char* rows_text);
+
+/* PartialOrderGraph::infer_strains(strains, read_pairs, n, e, tau, diff) (NonparametricClustering.cpp:704-708)
+ * and, when do_assign != 0, PartialOrderGraph::read_assign(strains, reads, read_pairs, n)
+ * (NonparametricClustering.cpp:776-836) followed by main()'s abundance sort (StrainCall.cpp:1027),
+ * for every subgroup.  Subgroups whose candidates were all pruned get status RAMBL_ERR_NO_STRAINS, and
+ * subgroups whose candidate set outgrew the kernels (more than 128 live strains, which needs
+ * degenerate abundances) get RAMBL_ERR_CAPACITY; the call itself still returns RAMBL_OK. */
+int rambl_batch_infer(rambl_batch* b, int32_t n, float e, float tau, float diff, int32_t do_assign, int32_t keep_loglik);
+
+/* ---- results */
+int32_t rambl_batch_num_subgroups(const rambl_batch* b);
+int32_t rambl_batch_num_nodes(const rambl_batch* b, int32_t sg);
+/* what = 0: one NODE line per node (id, state, label, level, ordered OUT / IN lists, ordered read pool);
+ * what = 1: PartialOrderGraph::output_edge (PartialOrderGraph.cpp:318-337), the -G output of StrainCall */
+char* rambl_batch_graph_text(const rambl_batch* b, int32_t sg, int32_t what);
+int32_t rambl_batch_status(const rambl_batch* b, int32_t sg);
+int32_t rambl_batch_num_strains(const rambl_batch* b, int32_t sg);
+/* strain k in the order streaming_clustering leaves them; order[] lists them by final abundance */
+int rambl_batch_strain(const rambl_batch* b, int32_t sg, int32_t k, double* abundance_infer, double* abundance,
+                       int32_t* path_len);
+int rambl_batch_strain_path(const rambl_batch* b, int32_t sg, int32_t k, int32_t* path);
+char* rambl_batch_strain_sequence(const rambl_batch* b, int32_t sg, int32_t k, int32_t plain); /* strain_seq / plain_seq */
+int rambl_batch_strain_sub(const rambl_batch* b, int32_t sg, int32_t k, double* sub36);
+int rambl_batch_strain_loglik(const rambl_batch* b, int32_t sg, int32_t k, double* loglik, int32_t n_reads);
+int rambl_batch_order(const rambl_batch* b, int32_t sg, int32_t* order);
+/* all of the above as text: STAGE/STRAIN/PATH/SEQ/PLAIN/SUB/LOGLIK lines (same layout as the oracle's dumps) */
+char* rambl_batch_strains_text(const rambl_batch* b, int32_t sg);
+/* the FASTA records StrainCall prints for this subgroup (StrainCall.cpp:1032-1046) */
+char* rambl_batch_fasta(const rambl_batch* b, int32_t sg, const char* gene_name, int32_t p0, int32_t p1, float tau);
+int rambl_batch_stats(const rambl_batch* b, rambl_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAMBL_B200_H */

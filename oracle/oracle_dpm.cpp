@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <limits>
 #include <queue>
 #include <random>
@@ -333,6 +334,12 @@ void infer_strains(const Pog& g, const PairTable& pairs, int n, LD e, LD tau, LD
         for (int v : nu.out) if (!queued.count(v)) { nxt.push(v); queued.insert(v); }
         if (!cur.empty()) continue;
 
+#ifdef ORACLE_TRACE
+        {
+            LD tot = 0; for (auto& s : level_strains) tot += s.abundance;
+            fprintf(stderr, "level strains=%zu reads=%zu branching=%d absum=%Lg\n", level_strains.size(), level_reads.size(), (int)branching, tot);
+        }
+#endif
         // ---- end of a level: update the per-read log-likelihood of every candidate strain
         if (!level_reads.empty())
         {

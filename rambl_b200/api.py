@@ -1,0 +1,361 @@
+"""Host-side mirror of StrainCall's in-memory interface over librambl_b200.so (include/rambl_b200.h).
+
+The names follow the reference (StrainCall/PartialOrderGraph.hpp:231-357,
+MultipleSequenceAlignment.hpp:87-107):
+
+    pog = PartialOrderGraph(G, R)                  # R: AlignRead tuples (pos, cigar, seq, qual, copies)
+    pog.output_edge()                              # the text StrainCall -G prints
+    strains = pog.infer_strains(read_pairs, n=5000, e=0.01, tau=0.02, diff=0.01)
+    pog.read_assign(strains, R, read_pairs, n=5000)
+    MultipleSequenceAlignmentSP().align(seqs)      # rows = MSA::get(t)
+
+plus ``StrainCallBatch`` for many subgroups at once (what scripts/rambl.py does with a process
+pool, rambl.py:165-194).  Everything computes on the GPU through the C ABI; there is no CPU
+fallback -- without the built library or without a device the calls raise ``RamblError``.
+This module imports only ctypes and numpy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librambl_b200.so")
+
+RAMBL_OK, RAMBL_ERR_CUDA, RAMBL_ERR_INVALID, RAMBL_ERR_CAPACITY, RAMBL_ERR_NO_STRAINS, RAMBL_ERR_STATE = range(6)
+
+
+class RamblError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("rambl_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [("gpu_launches", C.c_int32), ("level_steps", C.c_int32), ("draws", C.c_int64),
+                ("loglik_updates", C.c_int64), ("msa_dp_cells", C.c_int64), ("msa_problems", C.c_int32),
+                ("msa_kernel_ms", C.c_float), ("infer_gpu_ms", C.c_float), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64)]
+
+
+_lib: Optional[C.CDLL] = None
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+_strp = C.POINTER(C.c_char_p)
+
+# every symbol include/rambl_b200.h declares: (restype, argtypes)
+SYMBOLS = {
+    "rambl_last_error": (C.c_char_p, []),
+    "rambl_device_count": (C.c_int, []),
+    "rambl_free": (None, [C.c_void_p]),
+    "rambl_msa_rows_capacity": (C.c_int64, [C.c_int32, _i32p, _i32p]),
+    "rambl_msa_sp_align_batch": (C.c_int, [C.c_int32, _i32p, _i32p, C.c_char_p, _i32p, _i64p, _i32p, C.c_char_p,
+                                           C.POINTER(C.c_uint64), C.POINTER(C.c_float)]),
+    "rambl_batch_create": (C.c_void_p, []),
+    "rambl_batch_destroy": (None, [C.c_void_p]),
+    "rambl_batch_add_subgroup": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, _i32p, _strp, _strp, _i32p, _i32p, _i32p]),
+    "rambl_batch_build_graphs": (C.c_int, [C.c_void_p]),
+    "rambl_batch_thread_reads": (C.c_int, [C.c_void_p]),
+    "rambl_batch_msa_problems_text": (C.c_void_p, [C.c_void_p]),
+    "rambl_batch_finish_graphs_with_rows": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "rambl_batch_infer": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32]),
+    "rambl_batch_num_subgroups": (C.c_int32, [C.c_void_p]),
+    "rambl_batch_num_nodes": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "rambl_batch_graph_text": (C.c_void_p, [C.c_void_p, C.c_int32, C.c_int32]),
+    "rambl_batch_status": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "rambl_batch_num_strains": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "rambl_batch_strain": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _f64p, _f64p, _i32p]),
+    "rambl_batch_strain_path": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _i32p]),
+    "rambl_batch_strain_sequence": (C.c_void_p, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "rambl_batch_strain_sub": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _f64p]),
+    "rambl_batch_strain_loglik": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _f64p, C.c_int32]),
+    "rambl_batch_order": (C.c_int, [C.c_void_p, C.c_int32, _i32p]),
+    "rambl_batch_strains_text": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "rambl_batch_fasta": (C.c_void_p, [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int32, C.c_float]),
+    "rambl_batch_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load librambl_b200.so (built in-tree by __graft_entry__.build()); fail loudly when absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RamblError(RAMBL_ERR_CUDA, "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                             "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != RAMBL_OK:
+        raise RamblError(rc, (lib().rambl_last_error() or b"").decode())
+
+
+def _take(p) -> str:
+    if not p:
+        raise RamblError(RAMBL_ERR_INVALID, (lib().rambl_last_error() or b"").decode())
+    s = C.string_at(p).decode()
+    lib().rambl_free(p)
+    return s
+
+
+def _strs(xs: Sequence[str]):
+    arr = (C.c_char_p * max(1, len(xs)))()
+    for i, x in enumerate(xs):
+        arr[i] = x.encode()
+    return arr
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def device_count() -> int:
+    return lib().rambl_device_count()
+
+
+# ------------------------------------------------------------------------------------------------
+class MultipleSequenceAlignmentSP:
+    """MultipleSequenceAlignmentSP<Index2D,SimpleScoreModel,vector,string,char> with SimpleDnaScore defaults."""
+
+    def align(self, data: Sequence[str]) -> List[str]:
+        """Align ``data`` in order; row t of the result is MSA::get(t)."""
+        return msa_align_batch([list(data)])[0][0]
+
+
+def msa_align_batch(problems: Sequence[Sequence[str]]) -> Tuple[List[List[str]], Dict[str, float]]:
+    """Many independent alignments in one device launch -> (rows per problem, {dp_cells, kernel_ms})."""
+    L = lib()
+    P = len(problems)
+    pso = np.zeros(P + 1, dtype=np.int32)
+    seqs: List[str] = []
+    for p, pr in enumerate(problems):
+        seqs.extend(pr)
+        pso[p + 1] = len(seqs)
+    so = np.zeros(len(seqs) + 1, dtype=np.int32)
+    for i, s in enumerate(seqs):
+        so[i + 1] = so[i] + len(s)
+    letters = "".join(seqs).encode()
+    cap = L.rambl_msa_rows_capacity(P, pso.ctypes.data_as(_i32p), so.ctypes.data_as(_i32p))
+    rows = C.create_string_buffer(max(1, int(cap)))
+    width = np.zeros(max(P, 1), dtype=np.int32)
+    row_off = np.zeros(max(P, 1), dtype=np.int64)
+    stride = np.zeros(max(P, 1), dtype=np.int32)
+    cells = C.c_uint64(0)
+    ms = C.c_float(0)
+    _check(L.rambl_msa_sp_align_batch(P, pso.ctypes.data_as(_i32p), so.ctypes.data_as(_i32p), letters,
+                                      width.ctypes.data_as(_i32p), row_off.ctypes.data_as(_i64p),
+                                      stride.ctypes.data_as(_i32p), rows, C.byref(cells), C.byref(ms)))
+    raw = rows.raw
+    out: List[List[str]] = []
+    for p, pr in enumerate(problems):
+        base, st, w = int(row_off[p]), int(stride[p]), int(width[p])
+        out.append([raw[base + t * st: base + t * st + w].decode() for t in range(len(pr))])
+    return out, {"dp_cells": int(cells.value), "kernel_ms": float(ms.value)}
+
+
+# ------------------------------------------------------------------------------------------------
+class Strain:
+    """What StrainCall reads from a reference ``Strain``: abundance, path, strain_seq(), plain_seq()."""
+
+    def __init__(self, abundance_infer: float, abundance: float, path: List[int], seq: str, plain: str,
+                 sub: np.ndarray, loglik: Optional[np.ndarray]):
+        self.abundance_infer = abundance_infer
+        self.abundance = abundance
+        self.path = path
+        self._seq = seq
+        self._plain = plain
+        self.sub_count = sub  # 6x6 over A,C,G,T,-,=
+        self.read_loglik = loglik
+
+    def strain_seq(self) -> str:
+        return self._seq
+
+    def plain_seq(self) -> str:
+        return self._plain
+
+
+class StrainCallBatch:
+    """Any number of subgroups built and solved together on the device."""
+
+    def __init__(self):
+        self._h = lib().rambl_batch_create()
+        if not self._h:
+            raise RamblError(RAMBL_ERR_INVALID, "could not create a batch")
+        self._nreads: List[int] = []
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rambl_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_subgroup(self, gene: str, pos, cigar: Sequence[str], seq: Sequence[str], copies,
+                     pair_off=None, pair_val=None) -> int:
+        n = len(pos)
+        p, c = _i32(pos), _i32(copies)
+        po = _i32(pair_off) if pair_off is not None else None
+        pv = _i32(pair_val) if pair_val is not None else None
+        rc = lib().rambl_batch_add_subgroup(
+            self._h, gene.encode(), n, p.ctypes.data_as(_i32p), _strs(cigar), _strs(seq), c.ctypes.data_as(_i32p),
+            po.ctypes.data_as(_i32p) if po is not None else None, pv.ctypes.data_as(_i32p) if pv is not None else None)
+        if rc < 0:
+            _check(-rc)
+        self._nreads.append(n)
+        return rc
+
+    def add(self, sg) -> int:
+        """Add a rambl_b200.synth.Subgroup."""
+        return self.add_subgroup(sg.gene, sg.pos, sg.cigar, sg.seq, sg.cn, sg.pair_off, sg.pair_val)
+
+    def build_graphs(self):
+        _check(lib().rambl_batch_build_graphs(self._h))
+
+    # the construction with the device step supplied by the caller (see include/rambl_b200.h)
+    def thread_reads(self):
+        _check(lib().rambl_batch_thread_reads(self._h))
+
+    def msa_problems(self) -> List[List[str]]:
+        txt = _take(lib().rambl_batch_msa_problems_text(self._h))
+        out: List[List[str]] = []
+        lines = txt.split("\n")
+        i = 0
+        while i < len(lines):
+            if lines[i].startswith("P "):
+                n = int(lines[i].split()[2])
+                out.append(lines[i + 1:i + 1 + n])
+                i += 1 + n
+            else:
+                i += 1
+        return out
+
+    def finish_graphs_with_rows(self, rows: Sequence[Sequence[str]]):
+        txt = "".join("P %d %d\n%s\n" % (p, len(r), "\n".join(r)) for p, r in enumerate(rows))
+        _check(lib().rambl_batch_finish_graphs_with_rows(self._h, txt.encode()))
+
+    def infer(self, n: int = 5000, e: float = 0.01, tau: float = 0.02, diff: float = 0.01, assign: bool = True,
+              keep_loglik: bool = False):
+        _check(lib().rambl_batch_infer(self._h, n, e, tau, diff, int(assign), int(keep_loglik)))
+
+    # results ------------------------------------------------------------------------------------
+    def num_subgroups(self) -> int:
+        return lib().rambl_batch_num_subgroups(self._h)
+
+    def num_nodes(self, sg: int) -> int:
+        return lib().rambl_batch_num_nodes(self._h, sg)
+
+    def graph_dump(self, sg: int) -> str:
+        return _take(lib().rambl_batch_graph_text(self._h, sg, 0))
+
+    def output_edge(self, sg: int) -> str:
+        return _take(lib().rambl_batch_graph_text(self._h, sg, 1))
+
+    def status(self, sg: int) -> int:
+        return lib().rambl_batch_status(self._h, sg)
+
+    def strains_text(self, sg: int) -> str:
+        return _take(lib().rambl_batch_strains_text(self._h, sg))
+
+    def fasta(self, sg: int, gene_name: str, p0: int, p1: int, tau: float = 0.02) -> str:
+        return _take(lib().rambl_batch_fasta(self._h, sg, gene_name.encode(), p0, p1, tau))
+
+    def order(self, sg: int) -> List[int]:
+        n = lib().rambl_batch_num_strains(self._h, sg)
+        o = np.zeros(max(n, 1), dtype=np.int32)
+        _check(lib().rambl_batch_order(self._h, sg, o.ctypes.data_as(_i32p)))
+        return [int(x) for x in o[:n]]
+
+    def strains(self, sg: int, with_loglik: bool = False) -> List[Strain]:
+        L = lib()
+        n = L.rambl_batch_num_strains(self._h, sg)
+        if n < 0:
+            _check(-n)
+        out = []
+        for k in range(n):
+            a0, a1, pl = C.c_double(), C.c_double(), C.c_int32()
+            _check(L.rambl_batch_strain(self._h, sg, k, C.byref(a0), C.byref(a1), C.byref(pl)))
+            path = np.zeros(max(1, pl.value), dtype=np.int32)
+            _check(L.rambl_batch_strain_path(self._h, sg, k, path.ctypes.data_as(_i32p)))
+            sub = np.zeros(36, dtype=np.float64)
+            _check(L.rambl_batch_strain_sub(self._h, sg, k, sub.ctypes.data_as(_f64p)))
+            ll = None
+            if with_loglik:
+                ll = np.zeros(max(1, self._nreads[sg]), dtype=np.float64)
+                _check(L.rambl_batch_strain_loglik(self._h, sg, k, ll.ctypes.data_as(_f64p), self._nreads[sg]))
+            out.append(Strain(a0.value, a1.value, [int(x) for x in path[:pl.value]],
+                              _take(L.rambl_batch_strain_sequence(self._h, sg, k, 0)),
+                              _take(L.rambl_batch_strain_sequence(self._h, sg, k, 1)), sub.reshape(6, 6), ll))
+        return out
+
+    def stats(self) -> Dict[str, float]:
+        st = Stats()
+        _check(lib().rambl_batch_stats(self._h, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in Stats._fields_}
+
+
+# ------------------------------------------------------------------------------------------------
+class PartialOrderGraph:
+    """PartialOrderGraph(G, R) for one subgroup (PartialOrderGraph.hpp:231-357)."""
+
+    def __init__(self, G: str, R: Sequence[tuple]):
+        self._b = StrainCallBatch()
+        pos = [r[0] for r in R]
+        cigar = [r[1] for r in R]
+        seq = [r[2] for r in R]
+        cn = [r[4] if len(r) > 4 else 1 for r in R]
+        self._cn = cn
+        self._b.add_subgroup(G, pos, cigar, seq, cn)
+        self._b.build_graphs()
+        self._pairs = None
+
+    @property
+    def N(self) -> int:
+        return self._b.num_nodes(0)
+
+    def output_edge(self) -> str:
+        return self._b.output_edge(0)
+
+    def _set_pairs(self, read_pairs):
+        if read_pairs is None:
+            return
+        off = [0]
+        val: List[int] = []
+        for u in range(len(self._cn)):
+            mates = list(read_pairs.get(u, [-1] * self._cn[u])) if isinstance(read_pairs, dict) else list(read_pairs[u])
+            val.extend(mates)
+            off.append(len(val))
+        # the subgroup was added without pairs; rebuild it with them (graphs do not depend on pairs)
+        raise RamblError(RAMBL_ERR_STATE, "pass read_pairs to StrainCallBatch.add_subgroup for paired data")
+
+    def infer_strains(self, read_pairs=None, n: int = 5000, e: float = 0.01, tau: float = 0.02, diff: float = 0.01):
+        if read_pairs is not None:
+            self._set_pairs(read_pairs)
+        self._b.infer(n, e, tau, diff, assign=False)
+        if self._b.status(0) != RAMBL_OK:
+            raise RamblError(self._b.status(0), "every candidate strain was pruned")
+        return self._b.strains(0)
+
+    def read_assign(self, strains=None, reads=None, read_pairs=None, n: int = 5000, e: float = 0.01,
+                    tau: float = 0.02, diff: float = 0.01):
+        """infer_strains + read_assign + the abundance sort of StrainCall's main(); returns the sorted strains."""
+        self._b.infer(n, e, tau, diff, assign=True)
+        if self._b.status(0) != RAMBL_OK:
+            raise RamblError(self._b.status(0), "every candidate strain was pruned")
+        st = self._b.strains(0)
+        return [st[k] for k in self._b.order(0)]

@@ -1,0 +1,469 @@
+// extern "C" boundary of librambl_b200.so (declarations and reference citations: include/rambl_b200.h).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <sstream>
+
+#include "engine.hpp"
+#include "msa_sp.hpp"
+#include "pog.hpp"
+
+using namespace rambl;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg)
+{
+    g_error = msg;
+    return code;
+}
+
+template <typename F>
+int guarded(F&& f)
+{
+    try
+    {
+        f();
+        return RAMBL_OK;
+    }
+    catch (const Error& e) { return fail(e.code, e.what()); }
+    catch (const std::bad_alloc&) { return fail(RAMBL_ERR_CAPACITY, "out of host memory"); }
+    catch (const std::exception& e) { return fail(RAMBL_ERR_INVALID, e.what()); }
+}
+
+char* dup_text(const std::string& s)
+{
+    char* p = (char*)malloc(s.size() + 1);
+    if (p) memcpy(p, s.c_str(), s.size() + 1);
+    return p;
+}
+
+std::string fmt(double x)
+{
+    char b[64];
+    snprintf(b, sizeof b, "%.17g", x);
+    return b;
+}
+
+struct Subgroup
+{
+    std::string gene;
+    std::vector<AlignedRead> reads;
+    SubgroupInput input;
+    std::unique_ptr<GraphBuilder> builder;
+    FlatGraph graph;
+    bool built = false;
+    SubgroupResult result;
+    bool inferred = false;
+};
+
+}  // namespace
+
+struct rambl_batch
+{
+    std::vector<std::unique_ptr<Subgroup>> subs;
+    MsaBatch msa;
+    bool threaded = false;
+    size_t threaded_upto = 0;
+    rambl_stats stats;
+    InferParams last;
+    rambl_batch() { memset(&stats, 0, sizeof stats); }
+};
+
+namespace {
+
+void thread_pending(rambl_batch* b)
+{
+    for (size_t i = b->threaded_upto; i < b->subs.size(); ++i)
+    {
+        Subgroup& s = *b->subs[i];
+        s.builder.reset(new GraphBuilder);
+        s.builder->thread(s.gene, s.reads, b->msa);
+    }
+    b->threaded_upto = b->subs.size();
+}
+
+void finish_pending(rambl_batch* b, const MsaResult& rows)
+{
+    for (auto& sp : b->subs)
+    {
+        Subgroup& s = *sp;
+        if (s.built || !s.builder) continue;
+        s.builder->finish(rows, s.graph);
+        s.builder.reset();
+        s.input.graph = &s.graph;
+        s.built = true;
+    }
+    b->msa = MsaBatch();
+}
+
+const Subgroup* sub_at(const rambl_batch* b, int sg)
+{
+    if (!b || sg < 0 || sg >= (int)b->subs.size()) throw Error(RAMBL_ERR_INVALID, "subgroup index out of range");
+    return b->subs[sg].get();
+}
+
+const StrainResult& strain_at(const rambl_batch* b, int sg, int k)
+{
+    const Subgroup* s = sub_at(b, sg);
+    if (!s->inferred) throw Error(RAMBL_ERR_STATE, "rambl_batch_infer has not run");
+    if (k < 0 || k >= (int)s->result.strains.size()) throw Error(RAMBL_ERR_INVALID, "strain index out of range");
+    return s->result.strains[k];
+}
+
+void strains_block(std::ostringstream& os, const char* stage, const Subgroup& s, const std::vector<int>& order,
+                   bool infer_abundance, bool with_ll)
+{
+    os << "STAGE " << stage << " " << order.size() << "\n";
+    for (size_t i = 0; i < order.size(); ++i)
+    {
+        const StrainResult& r = s.result.strains[order[i]];
+        const double ab = infer_abundance ? r.abundance_infer : r.abundance;
+        double Z = 0;
+        for (int q = 0; q < 36; ++q) Z += r.sub[q];
+        os << "STRAIN " << i << " " << fmt(ab) << " " << fmt(ab) << " " << fmt(Z) << "\nPATH";
+        for (int u : r.path) os << " " << u;
+        os << "\nSEQ " << strain_sequence(s.graph, r.path) << "\nPLAIN " << strain_plain_sequence(s.graph, r.path) << "\nSUB";
+        for (int q = 0; q < 36; ++q) os << " " << fmt(r.sub[q]);
+        os << "\n";
+        if (with_ll && !r.loglik.empty())
+        {
+            os << "LOGLIK " << r.loglik.size();
+            for (size_t q = 0; q < r.loglik.size(); ++q) os << " " << q << ":" << fmt(r.loglik[q]);
+            os << "\n";
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rambl_last_error(void) { return g_error.c_str(); }
+
+int rambl_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void rambl_free(void* p) { free(p); }
+
+int64_t rambl_msa_rows_capacity(int32_t P, const int32_t* prob_seq_off, const int32_t* seq_off)
+{
+    int64_t total = 0;
+    for (int p = 0; p < P; ++p)
+    {
+        int64_t letters = 0;
+        for (int s = prob_seq_off[p]; s < prob_seq_off[p + 1]; ++s) letters += seq_off[s + 1] - seq_off[s];
+        const int64_t cap = std::min<int64_t>(std::max<int64_t>(letters, 1), MSA_WMAX);
+        total += cap * (prob_seq_off[p + 1] - prob_seq_off[p]);
+    }
+    return total;
+}
+
+int rambl_msa_sp_align_batch(int32_t P, const int32_t* prob_seq_off, const int32_t* seq_off, const char* letters,
+                             int32_t* width, int64_t* row_off, int32_t* row_stride, char* rows, uint64_t* dp_cells,
+                             float* kernel_ms)
+{
+    return guarded([&] {
+        if (P < 0 || (P > 0 && (!prob_seq_off || !seq_off || !width || !row_off || !row_stride || !rows)))
+            throw Error(RAMBL_ERR_INVALID, "null argument");
+        MsaBatch in;
+        in.prob_seq_off.assign(prob_seq_off, prob_seq_off + P + 1);
+        const int nseq = P ? prob_seq_off[P] : 0;
+        in.seq_off.assign(seq_off, seq_off + nseq + 1);
+        if (nseq && seq_off[nseq] > 0) in.chars.assign(letters, letters + seq_off[nseq]);
+        MsaResult out;
+        msa_sp_align_batch(in, out);
+        for (int p = 0; p < P; ++p) { width[p] = out.width[p]; row_off[p] = out.row_off[p]; row_stride[p] = out.cap[p]; }
+        if (!out.rows.empty()) memcpy(rows, out.rows.data(), out.rows.size());
+        if (dp_cells) *dp_cells = out.dp_cells;
+        if (kernel_ms) *kernel_ms = out.kernel_ms;
+    });
+}
+
+rambl_batch* rambl_batch_create(void)
+{
+    try { return new rambl_batch; }
+    catch (...) { return nullptr; }
+}
+
+void rambl_batch_destroy(rambl_batch* b) { delete b; }
+
+int rambl_batch_add_subgroup(rambl_batch* b, const char* gene, int32_t n_reads, const int32_t* pos,
+                             const char* const* cigar, const char* const* seq, const int32_t* copies,
+                             const int32_t* pair_off, const int32_t* pair_val)
+{
+    int index = -1;
+    int rc = guarded([&] {
+        if (!b || !gene || n_reads < 0 || (n_reads > 0 && (!pos || !cigar || !seq || !copies)))
+            throw Error(RAMBL_ERR_INVALID, "null argument");
+        std::unique_ptr<Subgroup> s(new Subgroup);
+        s->gene = gene;
+        s->reads.reserve(n_reads);
+        for (int i = 0; i < n_reads; ++i)
+        {
+            if (copies[i] < 1) throw Error(RAMBL_ERR_INVALID, "copy number must be >= 1");
+            s->reads.push_back({pos[i], cigar[i], seq[i], copies[i]});
+            s->input.read_cn.push_back(copies[i]);
+        }
+        if (pair_off && pair_val)
+        {
+            s->input.pair_off.assign(pair_off, pair_off + n_reads + 1);
+            s->input.pair_val.assign(pair_val, pair_val + pair_off[n_reads]);
+        }
+        else
+        {
+            s->input.pair_off.assign(1, 0);
+            for (int i = 0; i < n_reads; ++i)
+            {
+                s->input.pair_val.insert(s->input.pair_val.end(), copies[i], -1);
+                s->input.pair_off.push_back((int)s->input.pair_val.size());
+            }
+        }
+        b->subs.push_back(std::move(s));
+        index = (int)b->subs.size() - 1;
+    });
+    return rc == RAMBL_OK ? index : -rc;
+}
+
+int rambl_batch_thread_reads(rambl_batch* b)
+{
+    return guarded([&] {
+        if (!b) throw Error(RAMBL_ERR_INVALID, "null batch");
+        thread_pending(b);
+    });
+}
+
+char* rambl_batch_msa_problems_text(rambl_batch* b)
+{
+    if (!b) return nullptr;
+    std::ostringstream os;
+    const MsaBatch& m = b->msa;
+    for (int p = 0; p < m.problems(); ++p)
+    {
+        os << "P " << p << " " << (m.prob_seq_off[p + 1] - m.prob_seq_off[p]) << "\n";
+        for (int s = m.prob_seq_off[p]; s < m.prob_seq_off[p + 1]; ++s)
+            os << std::string(m.chars.data() + m.seq_off[s], m.chars.data() + m.seq_off[s + 1]) << "\n";
+    }
+    return dup_text(os.str());
+}
+
+int rambl_batch_finish_graphs_with_rows(rambl_batch* b, const char* rows_text)
+{
+    return guarded([&] {
+        if (!b || !rows_text) throw Error(RAMBL_ERR_INVALID, "null argument");
+        thread_pending(b);
+        MsaResult rows;
+        const int P = b->msa.problems();
+        rows.width.assign(P, 0); rows.cap.assign(P, 0); rows.row_off.assign(P + 1, 0);
+        std::istringstream is(rows_text);
+        std::string line;
+        int seen = 0;
+        while (std::getline(is, line))
+        {
+            if (line.empty()) continue;
+            int p = -1, n = 0;
+            if (sscanf(line.c_str(), "P %d %d", &p, &n) != 2 || p != seen || p >= P)
+                throw Error(RAMBL_ERR_INVALID, "rows text: expected 'P <index> <n>' in order");
+            if (n != b->msa.prob_seq_off[p + 1] - b->msa.prob_seq_off[p])
+                throw Error(RAMBL_ERR_INVALID, "rows text: wrong number of rows for a problem");
+            rows.row_off[p] = (long long)rows.rows.size();
+            for (int t = 0; t < n; ++t)
+            {
+                if (!std::getline(is, line)) throw Error(RAMBL_ERR_INVALID, "rows text: truncated");
+                if (t == 0) { rows.width[p] = (int)line.size(); rows.cap[p] = (int)line.size(); }
+                if ((int)line.size() != rows.width[p]) throw Error(RAMBL_ERR_INVALID, "rows text: ragged rows");
+                rows.rows.insert(rows.rows.end(), line.begin(), line.end());
+            }
+            ++seen;
+        }
+        if (seen != P) throw Error(RAMBL_ERR_INVALID, "rows text: missing problems");
+        rows.row_off[P] = (long long)rows.rows.size();
+        finish_pending(b, rows);
+    });
+}
+
+int rambl_batch_build_graphs(rambl_batch* b)
+{
+    return guarded([&] {
+        if (!b) throw Error(RAMBL_ERR_INVALID, "null batch");
+        require_device();
+        thread_pending(b);
+        MsaResult rows;
+        msa_sp_align_batch(b->msa, rows);
+        b->stats.gpu_launches += rows.launches;
+        b->stats.msa_dp_cells += (int64_t)rows.dp_cells;
+        b->stats.msa_problems += b->msa.problems();
+        b->stats.msa_kernel_ms += rows.kernel_ms;
+        b->stats.h2d_bytes += (int64_t)(b->msa.chars.size() + 4 * (b->msa.seq_off.size() + b->msa.prob_seq_off.size()));
+        b->stats.d2h_bytes += (int64_t)rows.rows.size();
+        finish_pending(b, rows);
+    });
+}
+
+int rambl_batch_infer(rambl_batch* b, int32_t n, float e, float tau, float diff, int32_t do_assign, int32_t keep_loglik)
+{
+    return guarded([&] {
+        if (!b) throw Error(RAMBL_ERR_INVALID, "null batch");
+        std::vector<SubgroupInput> in;
+        for (auto& sp : b->subs)
+        {
+            if (!sp->built) throw Error(RAMBL_ERR_STATE, "graphs are not built");
+            in.push_back(sp->input);
+        }
+        InferParams prm;
+        prm.n = n; prm.e = e; prm.tau = tau; prm.diff = diff; prm.assign = do_assign != 0; prm.keep_loglik = keep_loglik != 0;
+        std::vector<SubgroupResult> out;
+        EngineStats es;
+        infer_batch(in, prm, out, es);
+        for (size_t i = 0; i < out.size(); ++i) { b->subs[i]->result = std::move(out[i]); b->subs[i]->inferred = true; }
+        b->stats.gpu_launches += es.launches;
+        b->stats.level_steps += es.level_steps;
+        b->stats.draws += es.draws;
+        b->stats.loglik_updates += es.loglik_updates;
+        b->stats.infer_gpu_ms += es.gpu_ms;
+        b->last = prm;
+    });
+}
+
+int32_t rambl_batch_num_subgroups(const rambl_batch* b) { return b ? (int32_t)b->subs.size() : 0; }
+
+int32_t rambl_batch_num_nodes(const rambl_batch* b, int32_t sg)
+{
+    try { const Subgroup* s = sub_at(b, sg); return s->built ? s->graph.n_nodes : -RAMBL_ERR_STATE; }
+    catch (const Error& e) { return -fail(e.code, e.what()); }
+}
+
+char* rambl_batch_graph_text(const rambl_batch* b, int32_t sg, int32_t what)
+{
+    try
+    {
+        const Subgroup* s = sub_at(b, sg);
+        if (!s->built) throw Error(RAMBL_ERR_STATE, "graphs are not built");
+        return dup_text(what == 0 ? s->graph.dump() : s->graph.edges());
+    }
+    catch (const Error& e) { fail(e.code, e.what()); return nullptr; }
+}
+
+int32_t rambl_batch_status(const rambl_batch* b, int32_t sg)
+{
+    try { const Subgroup* s = sub_at(b, sg); return s->inferred ? s->result.status : RAMBL_ERR_STATE; }
+    catch (const Error& e) { return fail(e.code, e.what()); }
+}
+
+int32_t rambl_batch_num_strains(const rambl_batch* b, int32_t sg)
+{
+    try { const Subgroup* s = sub_at(b, sg); return s->inferred ? (int32_t)s->result.strains.size() : -RAMBL_ERR_STATE; }
+    catch (const Error& e) { return -fail(e.code, e.what()); }
+}
+
+int rambl_batch_strain(const rambl_batch* b, int32_t sg, int32_t k, double* abundance_infer, double* abundance,
+                       int32_t* path_len)
+{
+    return guarded([&] {
+        const StrainResult& r = strain_at(b, sg, k);
+        if (abundance_infer) *abundance_infer = r.abundance_infer;
+        if (abundance) *abundance = r.abundance;
+        if (path_len) *path_len = (int32_t)r.path.size();
+    });
+}
+
+int rambl_batch_strain_path(const rambl_batch* b, int32_t sg, int32_t k, int32_t* path)
+{
+    return guarded([&] {
+        const StrainResult& r = strain_at(b, sg, k);
+        for (size_t i = 0; i < r.path.size(); ++i) path[i] = r.path[i];
+    });
+}
+
+char* rambl_batch_strain_sequence(const rambl_batch* b, int32_t sg, int32_t k, int32_t plain)
+{
+    try
+    {
+        const StrainResult& r = strain_at(b, sg, k);
+        const Subgroup* s = sub_at(b, sg);
+        return dup_text(plain ? strain_plain_sequence(s->graph, r.path) : strain_sequence(s->graph, r.path));
+    }
+    catch (const Error& e) { fail(e.code, e.what()); return nullptr; }
+}
+
+int rambl_batch_strain_sub(const rambl_batch* b, int32_t sg, int32_t k, double* sub36)
+{
+    return guarded([&] { memcpy(sub36, strain_at(b, sg, k).sub, sizeof(double) * 36); });
+}
+
+int rambl_batch_strain_loglik(const rambl_batch* b, int32_t sg, int32_t k, double* loglik, int32_t n_reads)
+{
+    return guarded([&] {
+        const StrainResult& r = strain_at(b, sg, k);
+        if ((int)r.loglik.size() != n_reads) throw Error(RAMBL_ERR_STATE, "log-likelihood rows were not kept (keep_loglik) or size mismatch");
+        memcpy(loglik, r.loglik.data(), sizeof(double) * n_reads);
+    });
+}
+
+int rambl_batch_order(const rambl_batch* b, int32_t sg, int32_t* order)
+{
+    return guarded([&] {
+        const Subgroup* s = sub_at(b, sg);
+        if (!s->inferred) throw Error(RAMBL_ERR_STATE, "rambl_batch_infer has not run");
+        for (size_t i = 0; i < s->result.order.size(); ++i) order[i] = s->result.order[i];
+    });
+}
+
+char* rambl_batch_strains_text(const rambl_batch* b, int32_t sg)
+{
+    try
+    {
+        const Subgroup* s = sub_at(b, sg);
+        if (!s->inferred) throw Error(RAMBL_ERR_STATE, "rambl_batch_infer has not run");
+        std::ostringstream os;
+        std::vector<int> natural(s->result.strains.size());
+        for (size_t i = 0; i < natural.size(); ++i) natural[i] = (int)i;
+        strains_block(os, "infer", *s, natural, true, true);
+        if (b->last.assign)
+        {
+            strains_block(os, "assign", *s, natural, false, false);
+            strains_block(os, "final", *s, s->result.order, false, false);
+        }
+        return dup_text(os.str());
+    }
+    catch (const Error& e) { fail(e.code, e.what()); return nullptr; }
+}
+
+char* rambl_batch_fasta(const rambl_batch* b, int32_t sg, const char* gene_name, int32_t p0, int32_t p1, float tau)
+{
+    try
+    {
+        const Subgroup* s = sub_at(b, sg);
+        if (!s->inferred) throw Error(RAMBL_ERR_STATE, "rambl_batch_infer has not run");
+        std::ostringstream os;
+        int si = 0;
+        for (int k : s->result.order)
+        {
+            const StrainResult& r = s->result.strains[k];
+            // long double comparison against the float parameter in the reference (StrainCall.cpp:1035)
+            if (r.abundance >= (double)tau)
+                os << ">contig" << (gene_name ? gene_name : "") << p0 << p1 << si << "\n"
+                   << strain_plain_sequence(s->graph, r.path) << "\n";
+            ++si;
+        }
+        return dup_text(os.str());
+    }
+    catch (const Error& e) { fail(e.code, e.what()); return nullptr; }
+}
+
+int rambl_batch_stats(const rambl_batch* b, rambl_stats* out)
+{
+    if (!b || !out) return fail(RAMBL_ERR_INVALID, "null argument");
+    *out = b->stats;
+    return RAMBL_OK;
+}
+
+}  // extern "C"

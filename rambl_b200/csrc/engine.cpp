@@ -1,0 +1,685 @@
+// Host orchestration of the level-synchronous strain search (see engine.hpp).
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <random>
+#include <unordered_map>
+
+#include "dpm.cuh"
+
+namespace rambl {
+
+namespace {
+
+constexpr int kUniforms = 40000;  // a call never draws more: sweeps = min(n, 40000 / reads)
+
+// std::uniform draws of std::discrete_distribution on std::mt19937(1234): generate_canonical<double,53>
+// takes two 32-bit outputs, low word first (libstdc++ bits/random.tcc:3349-3381).
+std::vector<double> canonical_stream(int n)
+{
+    std::mt19937 gen(1234);
+    std::vector<double> u(n);
+    for (int i = 0; i < n; ++i)
+    {
+        const double lo = (double)gen(), hi = (double)gen();
+        double x = (lo + hi * 4294967296.0) / 18446744073709551616.0;
+        if (x >= 1.0) x = std::nextafter(1.0, 0.0);
+        u[i] = x;
+    }
+    return u;
+}
+
+struct Cand  // a candidate strain on the host: everything per-read lives in its device slot
+{
+    int slot = -1;
+    double ab = 0;
+    int tail = -1;   // index into Sub::trail
+    int node = -1;   // last node of the path
+    uint64_t hash = 1469598103934665603ull;  // of the concatenated labels (the reference keys maps by strain_seq)
+    uint64_t len = 0;
+};
+
+struct Sub
+{
+    const SubgroupInput* in = nullptr;
+    const FlatGraph* g = nullptr;
+    int R = 0;
+    // device state
+    DevBuf<double> ll, sub;
+    DevBuf<char> d_label, d_pool;
+    int slot_cap = 0;
+    std::vector<int> free_slots;
+    std::vector<char> retained;
+    // walk state
+    std::vector<Cand> cands;
+    std::vector<std::pair<int, int>> trail;  // (parent trail index, node)
+    std::vector<int> cur, nxt, mark;
+    int epoch = 0;
+    bool branching = false, done = false, failed = false;
+    std::vector<uint8_t> present;
+    int levels = 0;
+    // this step
+    int mode = MODE_NONE, m = 0, D = 0, read_size = 0, nsweeps = 0;
+    int ab_off = 0;
+    // result
+    bool have_result = false;
+    std::vector<Cand> result;
+    int status = RAMBL_OK;
+    long long draws = 0;
+};
+
+inline uint64_t extend_hash(uint64_t h, const char* s, int n)
+{
+    for (int i = 0; i < n; ++i) { h ^= (unsigned char)s[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+std::vector<int> path_of(const Sub& s, int tail)
+{
+    std::vector<int> p;
+    for (int t = tail; t >= 0; t = s.trail[t].first) p.push_back(s.trail[t].second);
+    std::reverse(p.begin(), p.end());
+    return p;
+}
+
+// seq_identity, NonparametricClustering.cpp:584-612
+double sequence_identity(const std::string& a, const std::string& b)
+{
+    int iden = 0, len = 0;
+    for (size_t i = 0; i < a.size(); ++i)
+    {
+        const char x = a[i], y = i < b.size() ? b[i] : '\0';
+        if ((x == '-' || x == '=') && (y == '-' || y == '=')) continue;
+        if (x == '^' && y == '^') continue;
+        if (x == y) iden += 1;
+        len += 1;
+    }
+    return (iden + 0.0) / len;
+}
+
+// std::sort with the reference's comparator on the same sequence: the same permutation, ties included
+template <typename T>
+void sort_desc_by_abundance(std::vector<T>& v)
+{
+    std::vector<int> idx(v.size());
+    for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) { return v[a].ab > v[b].ab; });
+    std::vector<T> r;
+    r.reserve(v.size());
+    for (int i : idx) r.push_back(v[i]);
+    v.swap(r);
+}
+
+struct Engine
+{
+    const InferParams& prm;
+    cudaStream_t st;
+    EngineStats& stats;
+    std::vector<Sub> subs;
+    double tau, diff, e;
+    // step staging
+    std::vector<StepGroup> h_groups;
+    std::vector<int> h_I;
+    std::vector<double> h_D;
+    std::vector<InheritOp> h_ops;
+    std::vector<int> group_sub;
+    DevBuf<StepGroup> d_groups;
+    DevBuf<int> d_I;
+    DevBuf<double> d_D, d_W, d_U;
+    DevBuf<InheritOp> d_ops;
+    long long w_total = 0, max_stride = 0;
+
+    Engine(const InferParams& p, cudaStream_t s, EngineStats& es) : prm(p), st(s), stats(es)
+    {
+        tau = (double)p.tau;
+        diff = (double)p.diff;
+        e = (double)p.e;
+    }
+
+    // ---- slots ---------------------------------------------------------------------------------
+    void grow_slots(Sub& s, int want)
+    {
+        if (want <= s.slot_cap) return;
+        int cap = std::max(s.slot_cap, 8);
+        while (cap < want) cap *= 2;
+        DevBuf<double> nll, nsub;
+        nll.reserve((size_t)cap * s.R);
+        nsub.reserve((size_t)cap * 36);
+        RAMBL_CUDA(cudaMemsetAsync(nll.p, 0, sizeof(double) * (size_t)cap * s.R, st));
+        launch_init_models(nsub.p, cap, e, st, &stats.launches);
+        if (s.slot_cap)
+        {
+            RAMBL_CUDA(cudaMemcpyAsync(nll.p, s.ll.p, sizeof(double) * (size_t)s.slot_cap * s.R, cudaMemcpyDeviceToDevice, st));
+            RAMBL_CUDA(cudaMemcpyAsync(nsub.p, s.sub.p, sizeof(double) * (size_t)s.slot_cap * 36, cudaMemcpyDeviceToDevice, st));
+        }
+        RAMBL_CUDA(cudaStreamSynchronize(st));
+        std::swap(s.ll.p, nll.p); std::swap(s.ll.cap, nll.cap);
+        std::swap(s.sub.p, nsub.p); std::swap(s.sub.cap, nsub.cap);
+        for (int k = cap - 1; k >= s.slot_cap; --k) s.free_slots.push_back(k);
+        s.retained.resize(cap, 0);
+        s.slot_cap = cap;
+    }
+    int take_slot(Sub& s)
+    {
+        if (s.free_slots.empty()) grow_slots(s, s.slot_cap + 1);
+        const int k = s.free_slots.back();
+        s.free_slots.pop_back();
+        return k;
+    }
+    void give_slot(Sub& s, int k)
+    {
+        if (k >= 0 && !s.retained[k]) s.free_slots.push_back(k);
+    }
+    void inherit(Sub& s, int src, int dst)
+    {
+        // grow_slots may have moved the buffers: ops are resolved to pointers at launch time
+        h_ops.push_back({nullptr, (long long)(&s - &subs[0]), nullptr, src, dst});
+    }
+
+    // ---- set-up --------------------------------------------------------------------------------
+    void start(const std::vector<SubgroupInput>& in)
+    {
+        subs.resize(in.size());
+        std::vector<double> u = canonical_stream(kUniforms);
+        d_U.reserve(kUniforms);
+        RAMBL_CUDA(cudaMemcpyAsync(d_U.p, u.data(), sizeof(double) * kUniforms, cudaMemcpyHostToDevice, st));
+        for (size_t i = 0; i < in.size(); ++i)
+        {
+            Sub& s = subs[i];
+            s.in = &in[i];
+            s.g = in[i].graph;
+            if (!s.g) throw Error(RAMBL_ERR_INVALID, "subgroup without a graph");
+            s.R = std::max(1, s.g->n_reads);
+            if ((int)in[i].read_cn.size() != s.g->n_reads || (int)in[i].pair_off.size() != s.g->n_reads + 1)
+                throw Error(RAMBL_ERR_INVALID, "read tables do not match the graph");
+            for (int r = 0; r < s.g->n_reads; ++r)
+                if (in[i].pair_off[r + 1] - in[i].pair_off[r] < in[i].read_cn[r])
+                    throw Error(RAMBL_ERR_INVALID, "ReadPairs needs one entry per read copy");
+            max_stride = std::max<long long>(max_stride, s.R);
+            s.d_label.reserve(std::max<size_t>(1, s.g->label_chars.size()));
+            s.d_pool.reserve(std::max<size_t>(1, s.g->pool_chars.size()));
+            if (!s.g->label_chars.empty())
+                RAMBL_CUDA(cudaMemcpyAsync(s.d_label.p, s.g->label_chars.data(), s.g->label_chars.size(), cudaMemcpyHostToDevice, st));
+            if (!s.g->pool_chars.empty())
+                RAMBL_CUDA(cudaMemcpyAsync(s.d_pool.p, s.g->pool_chars.data(), s.g->pool_chars.size(), cudaMemcpyHostToDevice, st));
+            grow_slots(s, 16);
+            s.present.assign(s.R, 0);
+            s.mark.assign(s.g->n_nodes, -1);
+            Cand root;  // Strain(100,e), NonparametricClustering.cpp:281
+            root.slot = take_slot(s);
+            s.cands.push_back(root);
+            s.cur.assign(1, 0);
+            if (s.g->n_nodes == 0) s.done = true;
+        }
+    }
+
+    // ---- "$": read_reassign's sort + merge_strains, NonparametricClustering.cpp:309-315,645-702 ----
+    void close_result(Sub& s)
+    {
+        std::vector<Cand> v = s.cands;
+        if (v.empty()) { s.status = RAMBL_ERR_NO_STRAINS; s.have_result = true; s.result.clear(); return; }
+        sort_desc_by_abundance(v);
+        sort_desc_by_abundance(v);  // merge_strains sorts again
+        std::vector<Cand> merged(1, v[0]);
+        std::vector<std::string> mseq(1, strain_sequence(*s.g, path_of(s, v[0].tail)));
+        for (size_t i = 1; i < v.size(); ++i)
+        {
+            const std::string q = strain_sequence(*s.g, path_of(s, v[i].tail));
+            size_t j = 0;
+            for (; j < merged.size(); ++j)
+                if (sequence_identity(q, mseq[j]) > 1 - diff) { merged[j].ab += v[i].ab; break; }
+            if (j == merged.size()) { merged.push_back(v[i]); mseq.push_back(q); }
+        }
+        // the reference copies the strains here; later levels (if any) must not touch the copies
+        for (Cand& c : s.result) if (c.slot >= 0) { s.retained[c.slot] = 0; s.free_slots.push_back(c.slot); }
+        for (Cand& c : merged)
+        {
+            const int k = take_slot(s);
+            inherit(s, c.slot, k);
+            c.slot = k;
+            s.retained[k] = 1;
+        }
+        s.result = merged;
+        s.have_result = true;
+        s.status = RAMBL_OK;
+    }
+
+    // ---- one level: host part before the launches ---------------------------------------------------
+    void prepare(Sub& s, int sub_index)
+    {
+        const FlatGraph& g = *s.g;
+        std::vector<int> lv_rid, lv_so, lv_sl, lv_cn;
+        s.nxt.clear();
+        for (int u : s.cur)
+        {
+            if (u == 0) { s.cands[0].tail = (int)s.trail.size(); s.trail.push_back({-1, 0}); s.cands[0].node = 0;
+                          s.cands[0].hash = extend_hash(s.cands[0].hash, g.label_chars.data() + g.label_off[0], g.label_off[1] - g.label_off[0]);
+                          s.cands[0].ab = 1; }
+            else if (g.label_off[u + 1] - g.label_off[u] == 1 && g.label_chars[g.label_off[u]] == '$') close_result(s);
+            else
+                for (int e2 = g.pool_off[u]; e2 < g.pool_off[u + 1]; ++e2)
+                {
+                    lv_rid.push_back(g.pool_rid[e2]);
+                    lv_so.push_back(g.pool_str_off[e2]);
+                    lv_sl.push_back(g.pool_str_off[e2 + 1] - g.pool_str_off[e2]);
+                    lv_cn.push_back(g.pool_cn[e2]);
+                }
+            for (int e2 = g.out_off[u]; e2 < g.out_off[u + 1]; ++e2)
+            {
+                const int v = g.out_to[e2];
+                if (s.mark[v] != s.epoch) { s.mark[v] = s.epoch; s.nxt.push_back(v); }
+            }
+        }
+        const int m = (int)lv_rid.size(), S = (int)s.cands.size();
+        s.m = m;
+        s.mode = (m > 0 && S > 0) ? (s.branching ? MODE_GIBBS : MODE_HARD) : MODE_NONE;
+        s.D = 0;
+        s.read_size = 0;
+        if (S > DPM_SMAX)
+        {   // only seen when the abundances have degenerated (NaN survives the reference's "< cut" pruning)
+            s.status = RAMBL_ERR_CAPACITY;
+            s.have_result = false;
+            s.failed = true;
+            s.done = true;
+            s.mode = MODE_NONE;
+            return;
+        }
+        if (s.mode == MODE_NONE) return;
+
+        StepGroup sg;
+        memset(&sg, 0, sizeof sg);
+        sg.ll = nullptr;  // resolved at launch
+        sg.S = S;
+        sg.m = m;
+        sg.mode = s.mode;
+        sg.slot_off = (int)h_I.size();
+        for (const Cand& c : s.cands) h_I.push_back(c.slot);
+        sg.lab_off = (int)h_I.size();
+        bool any_multi = false;
+        for (const Cand& c : s.cands) h_I.push_back(g.label_off[c.node]);
+        for (const Cand& c : s.cands)
+        {
+            const int l = g.label_off[c.node + 1] - g.label_off[c.node];
+            any_multi = any_multi || l > 1;
+            h_I.push_back(l);
+        }
+        sg.rid_off = (int)h_I.size();
+        h_I.insert(h_I.end(), lv_rid.begin(), lv_rid.end());
+        h_I.insert(h_I.end(), lv_so.begin(), lv_so.end());
+        h_I.insert(h_I.end(), lv_sl.begin(), lv_sl.end());
+        // "new" = first time any strain sees the read (read_loglik.count(rid)==0, line 364); the flag
+        // hard_clustering reads (new_reads, line 375) is only raised by strains on a collapsed node
+        for (int r = 0; r < m; ++r)
+        {
+            const bool fresh = !s.present[lv_rid[r]];
+            s.present[lv_rid[r]] = 1;
+            h_I.push_back(fresh ? 1 : 0);
+        }
+        if (s.mode == MODE_HARD && !any_multi)
+            for (int r = 0; r < m; ++r) h_I[sg.rid_off + 3 * m + r] = 0;
+        // draws: one per read copy, in read order, copies counted down (lines 36-39, 169-189)
+        int D = 0;
+        for (int r = 0; r < m; ++r) D += lv_cn[r];
+        sg.D = D;
+        sg.read_size = D;
+        sg.draw_off = (int)h_I.size();
+        h_I.resize(h_I.size() + 2 * (size_t)D);
+        int* dr = &h_I[sg.draw_off];
+        int* dm = dr + D;
+        int d = 0;
+        const SubgroupInput& in = *s.in;
+        for (int r = 0; r < m; ++r)
+            for (int cn = lv_cn[r]; cn > 0; --cn, ++d)
+            {
+                const int rid = lv_rid[r];
+                int mate = in.pair_val[in.pair_off[rid] + cn - 1];
+                if (mate >= s.R) throw Error(RAMBL_ERR_INVALID, "mate id out of range");
+                if (s.mode == MODE_GIBBS) { if (mate >= 0 && !s.present[mate]) mate = -1; }
+                dr[d] = r;
+                dm[d] = mate;
+            }
+        if (s.mode == MODE_HARD)  // Strain::logprob(uid) creates the entry (line 57)
+            for (int k = 0; k < D; ++k) if (dm[k] >= 0) s.present[dm[k]] = 1;
+        sg.nsweeps = (s.mode == MODE_GIBBS) ? std::min(prm.n, 40000 / D) : 0;
+        sg.ab_off = (int)h_D.size();
+        for (const Cand& c : s.cands) h_D.push_back(c.ab);
+        sg.w_off = w_total;
+        w_total += (long long)D * S;
+        s.D = D;
+        s.read_size = D;
+        s.nsweeps = sg.nsweeps;
+        s.ab_off = sg.ab_off;
+        h_groups.push_back(sg);
+        group_sub.push_back(sub_index);
+        stats.loglik_updates += (long long)m * S;
+        if (s.mode == MODE_GIBBS && S >= 2) { stats.draws += (long long)D * sg.nsweeps; s.draws += (long long)D * sg.nsweeps; }
+    }
+
+    // ---- one level: host part after the launches ------------------------------------------------------
+    void advance(Sub& s, const double* al)
+    {
+        const FlatGraph& g = *s.g;
+        std::vector<Cand>& cs = s.cands;
+        if (s.mode == MODE_GIBBS)
+        {
+            // abundance maps keyed by strain_seq (lines 404-429); equal sequences share an entry
+            std::unordered_map<uint64_t, double> before, after;
+            for (size_t i = 0; i < cs.size(); ++i) before[cs[i].hash ^ (cs[i].len * 0x9e3779b97f4a7c15ull)] = cs[i].ab;
+            for (size_t i = 0; i < cs.size(); ++i) cs[i].ab += al[i];
+            for (size_t i = 0; i < cs.size(); ++i) after[cs[i].hash ^ (cs[i].len * 0x9e3779b97f4a7c15ull)] = cs[i].ab;
+            double dmax = 0, Z = 0;
+            std::vector<double> delta(cs.size());
+            for (size_t i = 0; i < cs.size(); ++i)
+            {
+                const uint64_t k = cs[i].hash ^ (cs[i].len * 0x9e3779b97f4a7c15ull);
+                delta[i] = after[k] - before[k];
+                if (dmax < delta[i]) dmax = delta[i];
+                Z += al[i];
+            }
+            const double Zt = Z * tau;
+            std::vector<Cand> keep;
+            for (size_t i = 0; i < cs.size(); ++i)
+            {
+                if (al[i] < Zt || delta[i] < 0.01 * dmax) give_slot(s, cs[i].slot);
+                else keep.push_back(cs[i]);
+            }
+            cs.swap(keep);
+        }
+        else if (s.mode == MODE_HARD)
+            for (size_t i = 0; i < cs.size(); ++i) cs[i].ab += al[i];
+
+        // candidate strains of the next level (lines 473-551)
+        s.branching = false;
+        struct Child { Cand c; int parent; };
+        std::vector<Child> kids;
+        for (size_t i = 0; i < cs.size(); ++i)
+        {
+            const int v = cs[i].node;
+            const int e0 = g.out_off[v], e1 = g.out_off[v + 1];
+            double oz = 0, moc = 0;
+            for (int e2 = e0; e2 < e1; ++e2) { oz += g.out_cover[e2]; if (moc < g.out_cover[e2]) moc = g.out_cover[e2]; }
+            int dd = 0;
+            for (int e2 = e0; e2 < e1; ++e2)
+            {
+                const int o = g.out_to[e2];
+                const double oc = g.out_cover[e2];
+                Child k;
+                k.parent = (int)i;
+                k.c = cs[i];
+                if (o != g.end_node && oz > 0)
+                {
+                    if (oc <= 1. && oc < moc) { dd += 1; continue; }
+                    k.c.ab = (oc > 0) ? cs[i].ab * oc / oz : oz * std::min(0.01, tau);
+                }
+                k.c.node = o;
+                k.c.tail = (int)s.trail.size();
+                s.trail.push_back({cs[i].tail, o});
+                k.c.hash = extend_hash(cs[i].hash, g.label_chars.data() + g.label_off[o], g.label_off[o + 1] - g.label_off[o]);
+                k.c.len = cs[i].len + (uint64_t)(g.label_off[o + 1] - g.label_off[o]);
+                kids.push_back(k);
+            }
+            if (e1 - e0 > 1 + dd) s.branching = true;
+        }
+        if (kids.size() > 80)
+        {
+            std::vector<double> ssa;
+            for (const Child& k : kids) ssa.push_back(k.c.ab);
+            std::sort(ssa.begin(), ssa.end(), [](double x, double y) { return x > y; });
+            const double cut = ssa[80];
+            std::vector<Child> keep;
+            for (const Child& k : kids) if (!(k.c.ab < cut)) keep.push_back(k);
+            kids.swap(keep);
+        }
+        // slots: the first surviving child of a parent takes the parent's slot, the others copy it
+        std::vector<char> parent_used(cs.size(), 0);
+        std::vector<Cand> next;
+        next.reserve(kids.size());
+        for (Child& k : kids)
+        {
+            if (!parent_used[k.parent]) { parent_used[k.parent] = 1; k.c.slot = cs[k.parent].slot; }
+            else
+            {
+                const int dst = take_slot(s);
+                inherit(s, cs[k.parent].slot, dst);
+                k.c.slot = dst;
+            }
+            next.push_back(k.c);
+        }
+        for (size_t i = 0; i < cs.size(); ++i) if (!parent_used[i]) give_slot(s, cs[i].slot);
+        cs.swap(next);
+        s.cur.swap(s.nxt);
+        s.epoch += 1;
+        s.levels += 1;
+        if (s.cur.empty()) s.done = true;
+    }
+
+    void flush_inherits()
+    {
+        if (h_ops.empty()) return;
+        for (InheritOp& op : h_ops)
+        {
+            Sub& s = subs[(size_t)op.ll_stride];
+            op.ll = s.ll.p;
+            op.sub = s.sub.p;
+            op.ll_stride = s.R;
+        }
+        for (size_t b = 0; b < h_ops.size(); b += 32768)
+        {
+            const int n = (int)std::min<size_t>(32768, h_ops.size() - b);
+            d_ops.reserve(n);
+            RAMBL_CUDA(cudaMemcpyAsync(d_ops.p, h_ops.data() + b, sizeof(InheritOp) * n, cudaMemcpyHostToDevice, st));
+            launch_inherit(d_ops.p, n, max_stride, st, &stats.launches);
+            RAMBL_CUDA(cudaStreamSynchronize(st));  // h_ops / d_ops are reused
+        }
+        h_ops.clear();
+    }
+
+    void run_step(std::vector<double>& al)
+    {
+        flush_inherits();
+        al.clear();
+        if (h_groups.empty()) return;
+        int max_S = 0, max_m = 0, max_D = 0;
+        bool any_hard = false, any_gibbs = false;
+        for (size_t k = 0; k < h_groups.size(); ++k)
+        {
+            StepGroup& sg = h_groups[k];
+            Sub& s = subs[group_sub[k]];
+            sg.ll = s.ll.p;
+            sg.ll_stride = s.R;
+            sg.sub = s.sub.p;
+            sg.label_chars = s.d_label.p;
+            sg.pool_chars = s.d_pool.p;
+            max_S = std::max(max_S, sg.S);
+            max_m = std::max(max_m, sg.m);
+            max_D = std::max(max_D, sg.D);
+            any_hard = any_hard || sg.mode == MODE_HARD;
+            any_gibbs = any_gibbs || sg.mode == MODE_GIBBS || sg.mode == MODE_ASSIGN;
+        }
+        d_groups.reserve(h_groups.size());
+        d_I.reserve(std::max<size_t>(1, h_I.size()));
+        d_D.reserve(std::max<size_t>(1, h_D.size()));
+        d_W.reserve(std::max<long long>(1, w_total));
+        RAMBL_CUDA(cudaMemcpyAsync(d_groups.p, h_groups.data(), sizeof(StepGroup) * h_groups.size(), cudaMemcpyHostToDevice, st));
+        RAMBL_CUDA(cudaMemcpyAsync(d_I.p, h_I.data(), sizeof(int) * h_I.size(), cudaMemcpyHostToDevice, st));
+        RAMBL_CUDA(cudaMemcpyAsync(d_D.p, h_D.data(), sizeof(double) * h_D.size(), cudaMemcpyHostToDevice, st));
+        StepLaunch L;
+        L.groups = d_groups.p; L.n_groups = (int)h_groups.size(); L.iarena = d_I.p; L.darena = d_D.p;
+        L.weights = d_W.p; L.uniforms = d_U.p; L.n_uniforms = kUniforms;
+        L.max_S = max_S; L.max_m = max_m; L.max_D = max_D; L.any_hard = any_hard; L.any_gibbs = any_gibbs;
+        launch_level_step(L, st, &stats.launches);
+        al.resize(h_D.size());
+        RAMBL_CUDA(cudaMemcpyAsync(al.data(), d_D.p, sizeof(double) * h_D.size(), cudaMemcpyDeviceToHost, st));
+        RAMBL_CUDA(cudaStreamSynchronize(st));
+        stats.level_steps += 1;
+    }
+
+    void reset_step()
+    {
+        h_groups.clear(); h_I.clear(); h_D.clear(); group_sub.clear();
+        w_total = 0;
+    }
+
+    // ---- read_assign for every subgroup in one step, NonparametricClustering.cpp:776-836 ----
+    void assign_step(std::vector<double>& al)
+    {
+        reset_step();
+        for (size_t i = 0; i < subs.size(); ++i)
+        {
+            Sub& s = subs[i];
+            s.mode = MODE_NONE;
+            if (s.status != RAMBL_OK || s.result.empty()) continue;
+            const SubgroupInput& in = *s.in;
+            const int S = (int)s.result.size(), R = s.g->n_reads;
+            int D = 0;
+            for (int r = 0; r < R; ++r) D += in.read_cn[r];
+            if (D == 0) continue;
+            StepGroup sg;
+            memset(&sg, 0, sizeof sg);
+            sg.S = S; sg.m = R; sg.D = D; sg.mode = MODE_ASSIGN; sg.read_size = D;
+            sg.nsweeps = std::min(prm.n, 40000 / D);
+            sg.slot_off = (int)h_I.size();
+            for (const Cand& c : s.result) h_I.push_back(c.slot);
+            sg.lab_off = (int)h_I.size();
+            h_I.resize(h_I.size() + 2 * (size_t)S, 0);
+            sg.rid_off = (int)h_I.size();
+            for (int r = 0; r < R; ++r) h_I.push_back(r);
+            h_I.resize(h_I.size() + 3 * (size_t)R, 0);
+            sg.draw_off = (int)h_I.size();
+            h_I.resize(h_I.size() + 2 * (size_t)D);
+            int* dr = &h_I[sg.draw_off];
+            int* dm = dr + D;
+            int d = 0;
+            for (int r = 0; r < R; ++r)
+                for (int cn = in.read_cn[r]; cn > 0; --cn, ++d)
+                {
+                    dr[d] = r;
+                    dm[d] = in.pair_val[in.pair_off[r] + cn - 1];
+                    if (dm[d] >= s.R) throw Error(RAMBL_ERR_INVALID, "mate id out of range");
+                }
+            sg.ab_off = (int)h_D.size();
+            for (const Cand& c : s.result) h_D.push_back(c.ab);
+            sg.w_off = w_total;
+            w_total += (long long)D * S;
+            s.mode = MODE_ASSIGN;
+            s.ab_off = sg.ab_off;
+            h_groups.push_back(sg);
+            group_sub.push_back((int)i);
+            if (S >= 2) { stats.draws += (long long)D * sg.nsweeps; s.draws += (long long)D * sg.nsweeps; }
+        }
+        run_step(al);
+    }
+};
+
+}  // namespace
+
+std::string strain_sequence(const FlatGraph& g, const std::vector<int>& path)
+{
+    std::string r;
+    for (int u : path) r.append(g.label_chars.data() + g.label_off[u], g.label_chars.data() + g.label_off[u + 1]);
+    return r;
+}
+
+std::string strain_plain_sequence(const FlatGraph& g, const std::vector<int>& path)
+{
+    std::string r;
+    for (int u : path)
+    {
+        const std::string l = g.label(u);
+        if (l != "^" && l != "$" && l != "-" && l != "=") r += l;
+    }
+    return r;
+}
+
+void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, std::vector<SubgroupResult>& out,
+                 EngineStats& stats, cudaStream_t stream)
+{
+    require_device();
+    out.assign(in.size(), SubgroupResult());
+    if (in.empty()) return;
+    Engine E(prm, stream, stats);
+    cudaEvent_t e0, e1;
+    RAMBL_CUDA(cudaEventCreate(&e0));
+    RAMBL_CUDA(cudaEventCreate(&e1));
+    RAMBL_CUDA(cudaEventRecord(e0, stream));
+    E.start(in);
+    std::vector<double> al;
+    for (;;)
+    {
+        E.reset_step();
+        bool any = false;
+        for (size_t i = 0; i < E.subs.size(); ++i)
+        {
+            Sub& s = E.subs[i];
+            if (s.done) continue;
+            any = true;
+            E.prepare(s, (int)i);
+        }
+        if (!any) break;
+        E.run_step(al);
+        for (size_t i = 0; i < E.subs.size(); ++i)
+        {
+            Sub& s = E.subs[i];
+            if (s.done) continue;
+            E.advance(s, s.mode == MODE_NONE ? nullptr : al.data() + s.ab_off);
+        }
+    }
+    for (Sub& s : E.subs)
+        if (!s.have_result && !s.failed) s.status = RAMBL_ERR_NO_STRAINS;
+    std::vector<std::vector<double>> infer_ab(E.subs.size());
+    for (size_t i = 0; i < E.subs.size(); ++i)
+        for (const Cand& c : E.subs[i].result) infer_ab[i].push_back(c.ab);
+    if (prm.assign)
+    {
+        E.assign_step(al);
+        for (Sub& s : E.subs)
+            if (s.mode == MODE_ASSIGN)
+                for (size_t k = 0; k < s.result.size(); ++k) s.result[k].ab = al[s.ab_off + k];
+    }
+    else E.flush_inherits();
+    RAMBL_CUDA(cudaEventRecord(e1, stream));
+    // ---- gather
+    for (size_t i = 0; i < E.subs.size(); ++i)
+    {
+        Sub& s = E.subs[i];
+        SubgroupResult& r = out[i];
+        r.status = s.status;
+        r.draws = s.draws;
+        r.levels = s.levels;
+        if (s.status != RAMBL_OK) continue;
+        std::vector<double> subs_host((size_t)s.slot_cap * 36);
+        RAMBL_CUDA(cudaMemcpyAsync(subs_host.data(), s.sub.p, sizeof(double) * subs_host.size(), cudaMemcpyDeviceToHost, stream));
+        RAMBL_CUDA(cudaStreamSynchronize(stream));
+        for (size_t k = 0; k < s.result.size(); ++k)
+        {
+            StrainResult sr;
+            sr.abundance_infer = infer_ab[i][k];
+            sr.abundance = s.result[k].ab;
+            sr.path = path_of(s, s.result[k].tail);
+            memcpy(sr.sub, &subs_host[(size_t)s.result[k].slot * 36], sizeof(double) * 36);
+            if (prm.keep_loglik)
+            {
+                sr.loglik.resize(s.g->n_reads);
+                if (s.g->n_reads)
+                    RAMBL_CUDA(cudaMemcpyAsync(sr.loglik.data(), s.ll.p + (size_t)s.result[k].slot * s.R,
+                                               sizeof(double) * s.g->n_reads, cudaMemcpyDeviceToHost, stream));
+            }
+            r.strains.push_back(std::move(sr));
+        }
+        RAMBL_CUDA(cudaStreamSynchronize(stream));
+        r.order.resize(r.strains.size());
+        for (size_t k = 0; k < r.order.size(); ++k) r.order[k] = (int)k;
+        std::sort(r.order.begin(), r.order.end(), [&](int a, int b) { return r.strains[a].abundance > r.strains[b].abundance; });
+    }
+    RAMBL_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0;
+    RAMBL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    stats.gpu_ms += ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+}
+
+}  // namespace rambl

@@ -1,0 +1,69 @@
+// Strain inference over a batch of subgroups (host orchestration of the kernels in dpm.cu).
+//
+// Replaces, for every subgroup of the batch at once,
+//   PartialOrderGraph::infer_strains -> streaming_clustering  (NonparametricClustering.cpp:262-582,704-708)
+//   PartialOrderGraph::read_assign (AlignRead form)           (NonparametricClustering.cpp:776-836)
+//   the abundance sort of main()                              (StrainCall.cpp:1027)
+// The graph walk, the candidate bookkeeping (which strain extends over which edge, which strains
+// are dropped) and the final merge stay on the host -- they are a few hundred scalar decisions per
+// level -- while everything that is per read x strain runs on the device, level-synchronously over
+// all subgroups: one set of launches per graph level regardless of how many subgroups there are.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "pog.hpp"
+
+namespace rambl {
+
+struct InferParams
+{
+    int n = 5000;         // Gibbs sweeps cap, StrainCall.cpp:1021
+    float e = 0.01f;      // --error-rate   (held as float by the CLI, StrainCall.cpp:84)
+    float tau = 0.02f;    // --tau
+    float diff = 0.01f;   // --diff-rate
+    bool assign = true;   // run read_assign and the final sort
+    bool keep_loglik = false;  // also return the per-read log-likelihood rows of the inferred strains
+};
+
+struct StrainResult
+{
+    double abundance_infer = 0;  // after streaming_clustering (+ merge)
+    double abundance = 0;        // after read_assign (== abundance_infer when assign is off)
+    std::vector<int> path;       // node ids from "^" to "$"
+    double sub[36];              // substitution counts of the strain model
+    std::vector<double> loglik;  // [n_reads] when keep_loglik
+};
+
+struct SubgroupResult
+{
+    int status = 0;                     // RAMBL_OK or RAMBL_ERR_NO_STRAINS
+    std::vector<StrainResult> strains;  // order of streaming_clustering's result
+    std::vector<int> order;             // indices into strains, by abundance (StrainCall.cpp:1027)
+    long long draws = 0;                // categorical draws made for this subgroup
+    int levels = 0;
+};
+
+struct SubgroupInput
+{
+    const FlatGraph* graph = nullptr;
+    std::vector<int> read_cn;             // copy number per unique read
+    std::vector<int> pair_off, pair_val;  // ReadPairs as CSR over unique reads (one mate id or -1 per copy)
+};
+
+struct EngineStats
+{
+    int launches = 0;
+    int level_steps = 0;
+    long long draws = 0;
+    long long loglik_updates = 0;  // (read-pool entry, strain) pairs
+    float gpu_ms = 0;              // CUDA-event time from the first launch to the last
+};
+
+void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, std::vector<SubgroupResult>& out,
+                 EngineStats& stats, cudaStream_t stream = 0);
+
+std::string strain_sequence(const FlatGraph& g, const std::vector<int>& path);        // Strain::strain_seq
+std::string strain_plain_sequence(const FlatGraph& g, const std::vector<int>& path);  // Strain::plain_seq
+
+}  // namespace rambl

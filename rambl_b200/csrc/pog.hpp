@@ -1,0 +1,78 @@
+// Host side of the partial order graph: construction from aligned reads and the flat,
+// device-friendly form the clustering engine consumes.
+//
+// Mirrors the behaviour of the reference's PartialOrderGraph(G,R) constructor
+// (/root/reference/StrainCall/PartialOrderGraph.cpp:61-265) -- node order, ordered edge lists and
+// ordered read pools are reproduced exactly, because the strain search downstream depends on them --
+// but is organised for batching: construction is split in three phases so that the insertion
+// alignments of ALL levels of ALL subgroups go to the GPU in one launch (msa_sp.cu):
+//   phase A  thread(): splice every read into the backbone by its CIGAR, then list, per backbone
+//            level, the insertion strings that need a sum-of-pairs alignment;
+//   phase B  msa_sp_align_batch() on the device (not in this file);
+//   phase C  finish(): canonise insertions with the aligned rows, canonise deletions, merge equal
+//            siblings forward and backward, collapse linear paths, level the nodes, flatten.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "msa_sp.hpp"
+
+namespace rambl {
+
+enum : uint8_t { ST_MAT = 0, ST_MIS = 1, ST_INS = 2, ST_DEL = 3 };  // AlignState, PartialOrderGraph.hpp:82
+
+struct AlignedRead  // AlignRead, PartialOrderGraph.hpp:218 (the quality string is never used)
+{
+    int pos;
+    std::string cigar, seq;
+    int cn;
+};
+
+// The graph as arrays.  Node ids are the reference's ids (index into its `nodes` vector).
+struct FlatGraph
+{
+    int n_nodes = 0;
+    int n_reads = 0;                   // unique reads (rid range)
+    std::vector<uint8_t> st;           // AlignState per node
+    std::vector<int> level;            // LevelOrderIterator level (only output_edge prints it)
+    std::vector<int> label_off;        // n_nodes+1, into label_chars
+    std::vector<char> label_chars;
+    std::vector<int> out_off;          // n_nodes+1, CSR of ordered successors
+    std::vector<int> out_to;
+    std::vector<int> out_cover;        // number_of_reads_cover_nodes(u, v) per edge
+    std::vector<int> in_off;           // ordered predecessors (dump / parity only)
+    std::vector<int> in_from;
+    std::vector<int> pool_off;         // n_nodes+1, CSR of ordered read-pool entries
+    std::vector<int> pool_rid;
+    std::vector<int> pool_cn;
+    std::vector<int> pool_str_off;     // entries+1, into pool_chars
+    std::vector<char> pool_chars;
+    int end_node = -1;                 // id of "$"
+
+    std::string label(int u) const { return std::string(label_chars.data() + label_off[u], label_chars.data() + label_off[u + 1]); }
+    std::string pool_str(int e) const { return std::string(pool_chars.data() + pool_str_off[e], pool_chars.data() + pool_str_off[e + 1]); }
+    std::string dump() const;   // NODE lines in the format of oracle/ref_harness.cpp (without SIB)
+    std::string edges() const;  // PartialOrderGraph::output_edge
+};
+
+class GraphBuilder
+{
+public:
+    GraphBuilder();
+    ~GraphBuilder();
+    GraphBuilder(const GraphBuilder&) = delete;
+    GraphBuilder& operator=(const GraphBuilder&) = delete;
+
+    // phase A; appends this graph's alignment problems to `batch` and remembers where they start
+    void thread(const std::string& gene, const std::vector<AlignedRead>& reads, MsaBatch& batch);
+    // phase C; `rows` holds the solved problems of the batch that thread() appended to
+    void finish(const MsaResult& rows, FlatGraph& out);
+    int n_problems() const;
+
+private:
+    struct Impl;
+    Impl* m;
+};
+
+}  // namespace rambl

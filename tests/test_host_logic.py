@@ -1,0 +1,138 @@
+"""CPU: the C-ABI library loads and exports every declared symbol, the host graph construction of the
+product (phases A and C, with the device alignment step supplied by the test) equals the oracle's, and
+the product fails loudly -- never silently computes on the CPU -- when there is no device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from oracle import refpy
+from rambl_b200 import api, synth
+
+from helpers import ROOT, fuzz_spec, load_golden, strip_sib, subgroup_from_golden
+
+try:
+    HAVE_GPU = api.device_count() > 0
+except Exception:
+    HAVE_GPU = False
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rambl_b200.h")).read()
+    declared = set(re.findall(r"\b(rambl_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(api.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "missing export: " + name
+    assert declared == set(api.SYMBOLS), declared ^ set(api.SYMBOLS)
+    api.lib()
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "rambl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".hpp", ".cuh", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in txt and "refpy" not in txt and "import oracle" not in txt, f
+                assert "from oracle" not in txt, f
+
+
+def _build_with_supplied_rows(sg):
+    b = api.StrainCallBatch()
+    b.add(sg)
+    b.thread_reads()
+    probs = b.msa_problems()
+    b.finish_graphs_with_rows([refpy.msa_align(p, "oracle") for p in probs])
+    return b, len(probs)
+
+
+@pytest.mark.parametrize("seed", list(range(0, 24)))
+def test_graph_construction_matches_oracle(seed):
+    spec = fuzz_spec(seed)
+    spec["n_reads"] *= 2
+    sg = synth.make_subgroup(**spec)
+    if sg.n_unique == 0:
+        pytest.skip("no reads survived the filters")
+    b, _ = _build_with_supplied_rows(sg)
+    o = refpy.RefPog(sg.gene, sg.pos, sg.cigar, sg.seq, sg.cn, variant="oracle")
+    assert strip_sib(b.graph_dump(0)) == strip_sib(o.dump())
+    assert b.output_edge(0) == o.edges()
+
+
+def test_graph_construction_with_alignment_problems():
+    """Indel-rich homopolymer reads: several levels need the sum-of-pairs alignment."""
+    total = 0
+    for seed in (21, 35, 38, 16):
+        spec = dict(n_reads=600, read_len=60, n_strains=3, seed=seed, window=(100, 400), sub_err=0.005,
+                    indel_err=0.03, indel_frac=0.4, homopolymer_bias=True, divergence=(0.02, 0.06))
+        sg = synth.make_subgroup(**spec)
+        b, nprob = _build_with_supplied_rows(sg)
+        total += nprob
+        o = refpy.RefPog(sg.gene, sg.pos, sg.cigar, sg.seq, sg.cn, variant="oracle")
+        assert strip_sib(b.graph_dump(0)) == strip_sib(o.dump())
+        assert b.output_edge(0) == o.edges()
+    assert total > 0, "the cases were meant to exercise the alignment path"
+
+
+def test_graph_matches_golden_reference_dumps():
+    for case in load_golden("pog_golden.json"):
+        sg = subgroup_from_golden(case["input"])
+        b, _ = _build_with_supplied_rows(sg)
+        assert strip_sib(b.graph_dump(0)) == strip_sib(case["dump"]), case["name"]
+        assert b.output_edge(0) == case["edges"], case["name"]
+
+
+def test_empty_and_degenerate_inputs():
+    b = api.StrainCallBatch()
+    b.add_subgroup("ACGTACGT", [], [], [], [])  # no reads at all: backbone only
+    b.thread_reads()
+    assert b.msa_problems() == []
+    b.finish_graphs_with_rows([])
+    o = refpy.RefPog("ACGTACGT", [], [], [], [], variant="oracle")
+    assert b.output_edge(0) == o.edges()
+    # malformed input is refused, not guessed at
+    bad = api.StrainCallBatch()
+    bad.add_subgroup("ACGT", [0], ["9M"], ["ACGTACGTA"], [1])
+    with pytest.raises(api.RamblError) as ei:
+        bad.thread_reads()
+    assert ei.value.code == api.RAMBL_ERR_INVALID
+    with pytest.raises(api.RamblError):
+        api.StrainCallBatch().add_subgroup("ACGT", [0], ["4M"], ["ACGT"], [0])  # copy number 0
+
+
+def test_calls_in_wrong_order_are_errors():
+    b = api.StrainCallBatch()
+    b.add_subgroup("ACGTACGT", [0], ["8M"], ["ACGTACGT"], [1])
+    with pytest.raises(api.RamblError) as ei:
+        b.infer()
+    assert ei.value.code in (api.RAMBL_ERR_STATE, api.RAMBL_ERR_CUDA)
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="only meaningful on a box without a device")
+def test_no_device_is_a_loud_error():
+    with pytest.raises(api.RamblError) as ei:
+        api.msa_align_batch([["ACG", "A"]])
+    assert ei.value.code == api.RAMBL_ERR_CUDA
+    b = api.StrainCallBatch()
+    b.add_subgroup("ACGTACGT", [0], ["8M"], ["ACGTACGT"], [1])
+    with pytest.raises(api.RamblError) as ei:
+        b.build_graphs()
+    assert ei.value.code == api.RAMBL_ERR_CUDA
+    b2 = api.StrainCallBatch()
+    b2.add_subgroup("ACGTACGT", [0], ["8M"], ["ACGTACGT"], [1])
+    b2.thread_reads()
+    b2.finish_graphs_with_rows([])
+    with pytest.raises(api.RamblError) as ei:
+        b2.infer()
+    assert ei.value.code == api.RAMBL_ERR_CUDA
+
+
+def test_synthetic_downsampling_follows_std_mt19937():
+    """synth reproduces std::mt19937(1234) + uniform_real_distribution (StrainCall.cpp:491-493)."""
+    u = synth.StdMt19937(1234).canonical(3)
+    # first raw outputs of std::mt19937 seeded with 1234 (the standard fixes the sequence)
+    raw = synth.StdMt19937(1234).raw(2)
+    assert int(raw[0]) == 822569775 and int(raw[1]) == 2137449171
+    assert abs(u[0] - (822569775 + 2137449171 * 4294967296.0) / 18446744073709551616.0) < 1e-18
