@@ -44,6 +44,11 @@ typedef struct rambl_stats
     float infer_gpu_ms;       /* CUDA-event time of rambl_batch_infer, first launch to last */
     int64_t h2d_bytes;        /* bytes copied host->device / device->host by the library */
     int64_t d2h_bytes;
+    float gibbs_kernel_ms;    /* CUDA-event time inside the Gibbs-sweep kernel, summed over its launches */
+    int32_t gibbs_launches;
+    int64_t gibbs_alg_bytes;  /* sweeps x draws x (S weights + 1 uniform) x 8 bytes over those launches */
+    int64_t gibbs_rounds;     /* rounds of 32 speculative draws, and the passes it took to settle them */
+    int64_t gibbs_passes;
 } rambl_stats;
 
 const char* rambl_last_error(void);

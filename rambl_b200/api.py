@@ -38,7 +38,8 @@ class Stats(C.Structure):
     _fields_ = [("gpu_launches", C.c_int32), ("level_steps", C.c_int32), ("draws", C.c_int64),
                 ("loglik_updates", C.c_int64), ("msa_dp_cells", C.c_int64), ("msa_problems", C.c_int32),
                 ("msa_kernel_ms", C.c_float), ("infer_gpu_ms", C.c_float), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64)]
+                ("d2h_bytes", C.c_int64), ("gibbs_kernel_ms", C.c_float), ("gibbs_launches", C.c_int32),
+                ("gibbs_alg_bytes", C.c_int64), ("gibbs_rounds", C.c_int64), ("gibbs_passes", C.c_int64)]
 
 
 _lib: Optional[C.CDLL] = None

@@ -329,6 +329,13 @@ int rambl_batch_infer(rambl_batch* b, int32_t n, float e, float tau, float diff,
         b->stats.draws += es.draws;
         b->stats.loglik_updates += es.loglik_updates;
         b->stats.infer_gpu_ms += es.gpu_ms;
+        b->stats.h2d_bytes += es.h2d_bytes;
+        b->stats.d2h_bytes += es.d2h_bytes;
+        b->stats.gibbs_kernel_ms += es.gibbs_ms;
+        b->stats.gibbs_launches += es.gibbs_launches;
+        b->stats.gibbs_alg_bytes += es.gibbs_bytes;
+        b->stats.gibbs_rounds += es.gibbs_rounds;
+        b->stats.gibbs_passes += es.gibbs_passes;
         b->last = prm;
     });
 }

@@ -94,6 +94,50 @@ __global__ void __launch_bounds__(128) k_loglik(const StepGroup* __restrict__ gr
     }
 }
 
+// Scratch of one group inside the weights buffer (doubles, from w_off, which is a multiple of 32):
+//   [S][Dp] weights, strain-major, Dp = D rounded up to 32 so that the 32 draws of a Gibbs round are one
+//           aligned 256-byte run per strain (one bulk copy each); the padding is never read as data;
+//   [D]     normaliser per draw (k_hard);
+//   [D]     the read letter of every draw as an int code (k_gibbs statistics), stored in D double slots.
+__device__ __forceinline__ int padded_draws(int D) { return (D + 31) & ~31; }
+__device__ __forceinline__ double* group_weights(double* W, const StepGroup& g) { return W + g.w_off; }
+__device__ __forceinline__ double* group_norms(double* W, const StepGroup& g)
+{
+    return W + g.w_off + (long long)g.S * padded_draws(g.D);
+}
+__device__ __forceinline__ int* group_codes(double* W, const StepGroup& g)
+{
+    return reinterpret_cast<int*>(W + g.w_off + (long long)g.S * padded_draws(g.D) + g.D);
+}
+
+// ---- sm_90+/sm_100 bulk asynchronous copy (TMA without a tensor map) and its transaction barrier
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 __global__ void __launch_bounds__(128) k_weights(const StepGroup* __restrict__ groups, const int* __restrict__ I,
                                                  double* __restrict__ W)
 {
@@ -103,59 +147,75 @@ __global__ void __launch_bounds__(128) k_weights(const StepGroup* __restrict__ g
     const int r = I[g.draw_off + d];
     const int mate = I[g.draw_off + g.D + d];
     const int rid = I[g.rid_off + r];
-    double* w = W + g.w_off + (long long)d * g.S;
+    double* w = group_weights(W, g);
+    const int Dp = padded_draws(g.D);
     for (int s = 0; s < g.S; ++s)
     {
         const double* row = g.ll + (long long)I[g.slot_off + s] * g.ll_stride;
         double v = row[rid];
         if (mate >= 0) v += row[mate];
-        w[s] = exp(v);
+        w[(long long)s * Dp + d] = exp(v);
+    }
+    if (g.mode == MODE_GIBBS)
+    {
+        const int rl = I[g.rid_off + 2 * g.m + r];
+        group_codes(W, g)[d] = (rl == 1) ? letter_code(g.pool_chars[I[g.rid_off + g.m + r]]) : 7;
     }
 }
 
 // hard_clustering, NonparametricClustering.cpp:17-125: every read copy is spread over the strains by
 // its posterior; masses and substitution counts are summed and folded into the strain models.
+// Deterministic by construction (no atomics): pass 1 stores the normaliser of every draw, pass 2
+// gives each strain to one warp whose lanes stride over the draws with private accumulators and
+// combine them in a fixed shuffle tree.
 __global__ void __launch_bounds__(256) k_hard(const StepGroup* __restrict__ groups, const int* __restrict__ I,
-                                              double* __restrict__ Dar, const double* __restrict__ W)
+                                              double* __restrict__ Dar, double* __restrict__ W)
 {
     const StepGroup g = groups[blockIdx.x];
     if (g.mode != MODE_HARD) return;
-    __shared__ double acc[DPM_SMAX * 37];
     __shared__ double ab[DPM_SMAX];
-    const int tid = threadIdx.x, S = g.S;
-    for (int k = tid; k < S * 37; k += blockDim.x) acc[k] = 0;
+    const int tid = threadIdx.x, S = g.S, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const unsigned full = 0xffffffffu;
     for (int s = tid; s < S; s += blockDim.x) ab[s] = Dar[g.ab_off + s];
     __syncthreads();
+    double* T = group_norms(W, g);
+    const double* wt = group_weights(W, g);
+    const int Dp = padded_draws(g.D);
     for (int d = tid; d < g.D; d += blockDim.x)
     {
-        const double* w = W + g.w_off + (long long)d * S;
-        double T = 0;
-        for (int s = 0; s < S; ++s) T += ab[s] * w[s];
-        const int r = I[g.draw_off + d];
-        const char* rs = g.pool_chars + I[g.rid_off + g.m + r];
-        const int rl = I[g.rid_off + 2 * g.m + r];
-        const int isnew = I[g.rid_off + 3 * g.m + r];
-        for (int s = 0; s < S; ++s)
+        double t = 0;
+        for (int s = 0; s < S; ++s) t += ab[s] * wt[(long long)s * Dp + d];
+        T[d] = t;
+    }
+    __syncthreads();
+    for (int s = warp; s < S; s += nwarp)
+    {
+        double acc[37];
+#pragma unroll
+        for (int k = 0; k < 37; ++k) acc[k] = 0;
+        const char* lab = g.label_chars + I[g.lab_off + s];
+        const int lab_l = I[g.lab_off + S + s];
+        const int la = (lab_l == 1) ? letter_code(lab[0]) : 7;
+        const double a_s = ab[s];
+        for (int d = lane; d < g.D; d += 32)
         {
-            const double p = ab[s] * w[s] / T;
-            atomicAdd(&acc[s * 37], p);
-            const char* lab = g.label_chars + I[g.lab_off + s];
-            const int lab_l = I[g.lab_off + S + s];
+            const double p = a_s * wt[(long long)s * Dp + d] / T[d];
+            acc[0] += p;
+            const int r = I[g.draw_off + d];
+            const char* rs = g.pool_chars + I[g.rid_off + g.m + r];
+            const int rl = I[g.rid_off + 2 * g.m + r];
             if (rl == 1)
             {
-                if (lab_l == 1)
-                {
-                    const int a = letter_code(lab[0]), b = letter_code(rs[0]);
-                    if (a < 6 && b < 6) atomicAdd(&acc[s * 37 + 1 + a * 6 + b], p);
-                }
+                const int b = letter_code(rs[0]);
+                if (la < 6 && b < 6) acc[1 + la * 6 + b] += p;
             }
-            else if (isnew)
+            else if (I[g.rid_off + 3 * g.m + r])
             {
                 int ii = lab_l, jj = rl;
                 while (ii > 0 && jj > 0)
                 {
                     const int a = letter_code(lab[--ii]), b = letter_code(rs[--jj]);
-                    if (a < 6 && b < 6) atomicAdd(&acc[s * 37 + 1 + a * 6 + b], p);
+                    if (a < 6 && b < 6) acc[1 + a * 6 + b] += p;
                 }
             }
             else
@@ -164,108 +224,130 @@ __global__ void __launch_bounds__(256) k_hard(const StepGroup* __restrict__ grou
                 while (ii < lab_l && jj < rl)
                 {
                     const int a = letter_code(lab[ii++]), b = letter_code(rs[jj++]);
-                    if (a < 6 && b < 6) atomicAdd(&acc[s * 37 + 1 + a * 6 + b], p);
+                    if (a < 6 && b < 6) acc[1 + a * 6 + b] += p;
                 }
             }
         }
+        double* sub = g.sub + (long long)I[g.slot_off + s] * 36;
+        for (int k = 0; k < 37; ++k)
+        {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+            if (lane == 0)
+            {
+                if (k == 0) Dar[g.ab_off + s] = v;
+                else if (v != 0) sub[k - 1] += v;
+            }
+        }
     }
-    __syncthreads();
-    for (int k = tid; k < S * 36; k += blockDim.x)
-    {
-        const int s = k / 36, q = k % 36;
-        const double v = acc[s * 37 + 1 + q];
-        if (v != 0) g.sub[(long long)I[g.slot_off + s] * 36 + q] += v;
-    }
-    for (int s = tid; s < S; s += blockDim.x) Dar[g.ab_off + s] = acc[s * 37];
 }
 
 // np_bayes_clustering (NonparametricClustering.cpp:127-244) and read_assign (776-836): a sequential
-// Gibbs chain.  One warp per subgroup; lane l owns strains l, l+32, l+64, l+96.  Each draw multiplies
-// the strain masses by the read's weights, takes an inclusive scan in strain order, and picks the
-// first strain whose cumulative weight reaches u * total -- std::discrete_distribution's
-// lower_bound over the normalised partial sums (bits/random.tcc), with its rule that fewer than
-// two weights consume no random number.  u comes from the shared std::mt19937(1234) stream, which
-// the reference restarts on every call.
+// Gibbs chain -- draw t picks strain c with probability mass[c] * weight[c][read], then mass[c] += 1.
+// The draw is std::discrete_distribution's: first strain whose cumulative weight reaches u * total
+// (lower_bound over the normalised partial sums, bits/random.tcc), u from the shared
+// std::mt19937(1234) stream the reference restarts on every call, and no random number at all when
+// there are fewer than two strains.
+//
+// One warp per subgroup, 32 consecutive draws per round, one draw per lane, evaluated SPECULATIVELY
+// and then corrected to the exact sequential result: lane j computes its draw with the masses as
+// they would be after the draws of lanes < j *as currently guessed* (a ballot per strain gives the
+// prefix counts); the round repeats until no lane changes its answer.  Lane 0 is exact after the
+// first pass, and lane j is exact once lanes < j are, so the fixed point IS the sequential chain;
+// masses move by 1 in thousands, so two passes almost always suffice.  Cumulative sums run in
+// strain order in FP64, like the reference's accumulate/partial_sum.
 __global__ void __launch_bounds__(32) k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I,
-                                              double* __restrict__ Dar, const double* __restrict__ W,
-                                              const double* __restrict__ U)
+                                              double* __restrict__ Dar, double* __restrict__ W,
+                                              const double* __restrict__ U, unsigned long long* counters, int smem_S)
 {
     const StepGroup g = groups[blockIdx.x];
     if (g.mode != MODE_GIBBS && g.mode != MODE_ASSIGN) return;
-    __shared__ int cnt[DPM_SMAX * 8];
-    const int lane = threadIdx.x, S = g.S;
-    const unsigned full = 0xffffffffu;
+    extern __shared__ __align__(128) double gibbs_smem[];  // sized for the largest S of the launch (smem_S)
+    double* wbuf = gibbs_smem;                       // [2][strain][lane] weights of a round's 32 draws (bulk-copied)
+    double* cumbuf = wbuf + 2 * smem_S * 32;         // [strain][lane] cumulative weights
+    double* mass = cumbuf + smem_S * 32;             // [smem_S]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(mass + smem_S);  // [2]
+    int* cnt = reinterpret_cast<int*>(bars + 2);     // [smem_S][8]
+    int* hist = cnt + smem_S * 8;                    // [smem_S]
+    const int lane = threadIdx.x, S = g.S, D = g.D;
+    const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+    const double* wt = group_weights(W, g);
+    const int* code = group_codes(W, g);
+    const int Dp = padded_draws(D);
     for (int k = lane; k < S * 8; k += 32) cnt[k] = 0;
-    double a[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) a[k] = (lane + 32 * k < S) ? Dar[g.ab_off + lane + 32 * k] : 0.0;
+    for (int s = lane; s < S; s += 32) { mass[s] = Dar[g.ab_off + s]; hist[s] = 0; }
+    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    const int nblk = (S + 31) / 32;
-    int ui = 0;
-    for (int sweep = 0; sweep < g.nsweeps; ++sweep)
+    const int per_sweep = Dp / 32;
+    const long long n_rounds = (S >= 2) ? (long long)g.nsweeps * per_sweep : 0;
+    unsigned long long rounds = 0, passes = 0;
+    // stage the weights of round r: S rows of 32 consecutive draws, 256 B each, one bulk copy per row
+    auto stage = [&](long long r) {
+        const int b = (int)(r & 1);
+        const int blk = (int)(r % per_sweep);
+        if (lane == 0) mbar_expect_tx(&bars[b], (unsigned)S * 256u);
+        __syncwarp();
+        for (int s = lane; s < S; s += 32)
+            bulk_g2s(wbuf + ((size_t)b * smem_S + s) * 32, wt + (long long)s * Dp + blk * 32, 256u, &bars[b]);
+    };
+    if (n_rounds > 0) stage(0);
+    for (long long r = 0; r < n_rounds; ++r)
     {
-        for (int d = 0; d < g.D; ++d)
+        const int sweep = (int)(r / per_sweep), blk = (int)(r % per_sweep);
+        const int d = blk * 32 + lane;
+        const bool valid = d < D;
+        const double u = valid ? U[(long long)sweep * D + d] : 0.0;
+        const int cd = (valid && g.mode == MODE_GIBBS) ? code[d] : 0;
+        if (r + 1 < n_rounds) stage(r + 1);  // overlaps this round's arithmetic
+        mbar_wait(&bars[r & 1], (unsigned)((r >> 1) & 1));
+        const double* wl = wbuf + (size_t)(r & 1) * smem_S * 32 + lane;
+        double* cl = cumbuf + lane;
+        int c = -1;
+        for (;;)
         {
-            const double* w = W + g.w_off + (long long)d * S;
-            double cum[4];
-            double carry = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
+            double cum = 0;
+#pragma unroll 4
+            for (int s = 0; s < S; ++s)
             {
-                if (k < nblk)
-                {
-                    const int s = lane + 32 * k;
-                    double x = (s < S) ? a[k] * w[s] : 0.0;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1)
-                    {
-                        const double y = __shfl_up_sync(full, x, o);
-                        if (lane >= o) x += y;
-                    }
-                    cum[k] = x + carry;
-                    carry = __shfl_sync(full, cum[k], 31);
-                }
+                const unsigned m = __ballot_sync(full, c == s);
+                const double as = mass[s] + (double)__popc(m & lt);
+                cum = fma(as, wl[s * 32], cum);
+                cl[s * 32] = cum;
             }
-            int c = 0;
-            if (S >= 2)
-            {
-                const double t = U[ui++] * carry;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (k < nblk)
-                    {
-                        const bool below = (lane + 32 * k < S) && (cum[k] < t);
-                        c += __popc(__ballot_sync(full, below));
-                    }
-                if (c > S - 1) c = S - 1;
-            }
-            if (lane == (c & 31))
-            {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) if (k == (c >> 5)) a[k] += 1.0;
-                if (g.mode == MODE_GIBBS)
-                {
-                    const int r = I[g.draw_off + d];
-                    const int rl = I[g.rid_off + 2 * g.m + r];
-                    const int b = (rl == 1) ? letter_code(g.pool_chars[I[g.rid_off + g.m + r]]) : 7;
-                    cnt[c * 8 + b] += 1;
-                }
-            }
+            const double thr = u * cum;
+            int cn = 0;
+#pragma unroll 4
+            for (int s = 0; s < S; ++s) cn += (cl[s * 32] < thr) ? 1 : 0;
+            if (cn > S - 1) cn = S - 1;
+            if (!valid) cn = -1;
+            const bool changed = __any_sync(full, cn != c);
+            c = cn;
+            ++passes;
+            if (!changed) break;
         }
+        ++rounds;
+        if (valid)
+        {
+            atomicAdd(&hist[c], 1);
+            if (g.mode == MODE_GIBBS) atomicAdd(&cnt[c * 8 + cd], 1);
+        }
+        __syncwarp();
+        for (int s = lane; s < S; s += 32) { mass[s] += (double)hist[s]; hist[s] = 0; }
+        __syncwarp();
+    }
+    if (lane == 0 && counters)
+    {
+        atomicAdd(&counters[0], rounds);
+        atomicAdd(&counters[1], passes);
     }
     // normalise the masses; fold the averaged counts into the models (lines 217-243)
     double z = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) z += a[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(full, z, o);
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int s = 0; s < S; ++s) z += mass[s];
+    for (int s = lane; s < S; s += 32)
     {
-        const int s = lane + 32 * k;
-        if (s >= S) continue;
-        double v = a[k] / z;
+        double v = mass[s] / z;
         if (g.mode == MODE_GIBBS) v *= (double)g.read_size;
         Dar[g.ab_off + s] = v;
         if (g.mode == MODE_GIBBS && I[g.lab_off + S + s] == 1)
@@ -321,7 +403,17 @@ void launch_level_step(const StepLaunch& L, cudaStream_t st, int* launches)
     }
     if (L.any_gibbs)
     {
-        k_gibbs<<<L.n_groups, 32, 0, st>>>(L.groups, L.iarena, L.darena, L.weights, L.uniforms);
+        if (L.gibbs_begin) RAMBL_CUDA(cudaEventRecord(L.gibbs_begin, st));
+        const int smem_S = (L.max_S + 3) & ~3;
+        const size_t smem = sizeof(double) * ((size_t)smem_S * 97 + 2) + sizeof(int) * ((size_t)smem_S * 9);
+        static size_t configured = 0;
+        if (smem > configured)
+        {
+            RAMBL_CUDA(cudaFuncSetAttribute(k_gibbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        k_gibbs<<<L.n_groups, 32, smem, st>>>(L.groups, L.iarena, L.darena, L.weights, L.uniforms, L.counters, smem_S);
+        if (L.gibbs_end) RAMBL_CUDA(cudaEventRecord(L.gibbs_end, st));
         ++*launches;
     }
     RAMBL_CUDA(cudaGetLastError());

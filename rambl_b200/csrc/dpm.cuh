@@ -60,6 +60,8 @@ struct StepLaunch
     int n_uniforms;
     int max_S, max_m, max_D;
     bool any_hard, any_gibbs;
+    unsigned long long* counters = nullptr;  // device, [0] rounds of 32 draws, [1] passes over those rounds
+    cudaEvent_t gibbs_begin = nullptr, gibbs_end = nullptr;  // optional: bracket the k_gibbs launch
 };
 
 void launch_level_step(const StepLaunch& L, cudaStream_t st, int* launches);

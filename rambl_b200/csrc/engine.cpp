@@ -32,6 +32,13 @@ std::vector<double> canonical_stream(int n)
     return u;
 }
 
+// per-group scratch in the weights buffer (layout in dpm.cu): [S][D padded to 32] + [D] + [D], kept 256-byte aligned
+inline long long scratch_doubles(int S, int D)
+{
+    const long long Dp = (D + 31) & ~31;
+    return ((long long)S * Dp + 2LL * D + 31) & ~31LL;
+}
+
 struct Cand  // a candidate strain on the host: everything per-read lives in its device slot
 {
     int slot = -1;
@@ -130,7 +137,9 @@ struct Engine
     DevBuf<int> d_I;
     DevBuf<double> d_D, d_W, d_U;
     DevBuf<InheritOp> d_ops;
+    DevBuf<unsigned long long> d_counters;
     long long w_total = 0, max_stride = 0;
+    std::vector<cudaEvent_t> gibbs_events;  // pairs, resolved after the last step
 
     Engine(const InferParams& p, cudaStream_t s, EngineStats& es) : prm(p), st(s), stats(es)
     {
@@ -185,6 +194,8 @@ struct Engine
         subs.resize(in.size());
         std::vector<double> u = canonical_stream(kUniforms);
         d_U.reserve(kUniforms);
+        d_counters.reserve(2);
+        RAMBL_CUDA(cudaMemsetAsync(d_counters.p, 0, 2 * sizeof(unsigned long long), st));
         RAMBL_CUDA(cudaMemcpyAsync(d_U.p, u.data(), sizeof(double) * kUniforms, cudaMemcpyHostToDevice, st));
         for (size_t i = 0; i < in.size(); ++i)
         {
@@ -205,6 +216,7 @@ struct Engine
                 RAMBL_CUDA(cudaMemcpyAsync(s.d_label.p, s.g->label_chars.data(), s.g->label_chars.size(), cudaMemcpyHostToDevice, st));
             if (!s.g->pool_chars.empty())
                 RAMBL_CUDA(cudaMemcpyAsync(s.d_pool.p, s.g->pool_chars.data(), s.g->pool_chars.size(), cudaMemcpyHostToDevice, st));
+            stats.h2d_bytes += (long long)(s.g->label_chars.size() + s.g->pool_chars.size());
             grow_slots(s, 16);
             s.present.assign(s.R, 0);
             s.mark.assign(s.g->n_nodes, -1);
@@ -347,7 +359,7 @@ struct Engine
         sg.ab_off = (int)h_D.size();
         for (const Cand& c : s.cands) h_D.push_back(c.ab);
         sg.w_off = w_total;
-        w_total += (long long)D * S;
+        w_total += scratch_doubles(S, D);  // weights, normalisers (k_hard), letter codes (k_gibbs)
         s.D = D;
         s.read_size = D;
         s.nsweeps = sg.nsweeps;
@@ -471,6 +483,7 @@ struct Engine
             const int n = (int)std::min<size_t>(32768, h_ops.size() - b);
             d_ops.reserve(n);
             RAMBL_CUDA(cudaMemcpyAsync(d_ops.p, h_ops.data() + b, sizeof(InheritOp) * n, cudaMemcpyHostToDevice, st));
+            stats.h2d_bytes += (long long)sizeof(InheritOp) * n;
             launch_inherit(d_ops.p, n, max_stride, st, &stats.launches);
             RAMBL_CUDA(cudaStreamSynchronize(st));  // h_ops / d_ops are reused
         }
@@ -508,13 +521,47 @@ struct Engine
         RAMBL_CUDA(cudaMemcpyAsync(d_D.p, h_D.data(), sizeof(double) * h_D.size(), cudaMemcpyHostToDevice, st));
         StepLaunch L;
         L.groups = d_groups.p; L.n_groups = (int)h_groups.size(); L.iarena = d_I.p; L.darena = d_D.p;
-        L.weights = d_W.p; L.uniforms = d_U.p; L.n_uniforms = kUniforms;
+        L.weights = d_W.p; L.uniforms = d_U.p; L.n_uniforms = kUniforms; L.counters = d_counters.p;
         L.max_S = max_S; L.max_m = max_m; L.max_D = max_D; L.any_hard = any_hard; L.any_gibbs = any_gibbs;
+        if (any_gibbs)
+        {
+            cudaEvent_t a, b;
+            RAMBL_CUDA(cudaEventCreate(&a));
+            RAMBL_CUDA(cudaEventCreate(&b));
+            gibbs_events.push_back(a);
+            gibbs_events.push_back(b);
+            L.gibbs_begin = a;
+            L.gibbs_end = b;
+            stats.gibbs_launches += 1;
+            for (const StepGroup& sg : h_groups)
+                if ((sg.mode == MODE_GIBBS || sg.mode == MODE_ASSIGN) && sg.S >= 2)
+                    stats.gibbs_bytes += (long long)sg.nsweeps * sg.D * (sg.S + 1) * 8;
+        }
+        stats.h2d_bytes += (long long)(sizeof(StepGroup) * h_groups.size() + sizeof(int) * h_I.size() + sizeof(double) * h_D.size());
+        stats.d2h_bytes += (long long)(sizeof(double) * h_D.size());
         launch_level_step(L, st, &stats.launches);
         al.resize(h_D.size());
         RAMBL_CUDA(cudaMemcpyAsync(al.data(), d_D.p, sizeof(double) * h_D.size(), cudaMemcpyDeviceToHost, st));
         RAMBL_CUDA(cudaStreamSynchronize(st));
         stats.level_steps += 1;
+    }
+
+    void collect_kernel_times()
+    {
+        for (size_t k = 0; k + 1 < gibbs_events.size(); k += 2)
+        {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, gibbs_events[k], gibbs_events[k + 1]) == cudaSuccess) stats.gibbs_ms += ms;
+            cudaEventDestroy(gibbs_events[k]);
+            cudaEventDestroy(gibbs_events[k + 1]);
+        }
+        gibbs_events.clear();
+        unsigned long long c[2] = {0, 0};
+        if (d_counters.p && cudaMemcpy(c, d_counters.p, sizeof c, cudaMemcpyDeviceToHost) == cudaSuccess)
+        {
+            stats.gibbs_rounds += (long long)c[0];
+            stats.gibbs_passes += (long long)c[1];
+        }
     }
 
     void reset_step()
@@ -563,7 +610,7 @@ struct Engine
             sg.ab_off = (int)h_D.size();
             for (const Cand& c : s.result) h_D.push_back(c.ab);
             sg.w_off = w_total;
-            w_total += (long long)D * S;
+            w_total += scratch_doubles(S, D);
             s.mode = MODE_ASSIGN;
             s.ab_off = sg.ab_off;
             h_groups.push_back(sg);
@@ -641,6 +688,8 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
     }
     else E.flush_inherits();
     RAMBL_CUDA(cudaEventRecord(e1, stream));
+    RAMBL_CUDA(cudaStreamSynchronize(stream));
+    E.collect_kernel_times();
     // ---- gather
     for (size_t i = 0; i < E.subs.size(); ++i)
     {
@@ -652,6 +701,7 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
         if (s.status != RAMBL_OK) continue;
         std::vector<double> subs_host((size_t)s.slot_cap * 36);
         RAMBL_CUDA(cudaMemcpyAsync(subs_host.data(), s.sub.p, sizeof(double) * subs_host.size(), cudaMemcpyDeviceToHost, stream));
+        stats.d2h_bytes += (long long)sizeof(double) * subs_host.size();
         RAMBL_CUDA(cudaStreamSynchronize(stream));
         for (size_t k = 0; k < s.result.size(); ++k)
         {

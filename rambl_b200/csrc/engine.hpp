@@ -58,6 +58,11 @@ struct EngineStats
     long long draws = 0;
     long long loglik_updates = 0;  // (read-pool entry, strain) pairs
     float gpu_ms = 0;              // CUDA-event time from the first launch to the last
+    float gibbs_ms = 0;            // CUDA-event time spent inside the Gibbs kernel, summed over its launches
+    int gibbs_launches = 0;
+    long long gibbs_bytes = 0;     // algorithmic bytes of those launches: sweeps x draws x (S weights + 1 uniform) x 8
+    long long h2d_bytes = 0, d2h_bytes = 0;
+    long long gibbs_rounds = 0, gibbs_passes = 0;  // rounds of 32 speculative draws / passes needed to settle them
 };
 
 void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, std::vector<SubgroupResult>& out,
