@@ -95,12 +95,15 @@ __global__ void __launch_bounds__(128) k_loglik(const StepGroup* __restrict__ gr
 }
 
 // Scratch of one group inside the weights buffer (doubles, from w_off, which is a multiple of 32):
-//   [S][Dp] weights, strain-major, Dp = D rounded up to 32 so that the 32 draws of a Gibbs round are one
-//           aligned 256-byte run per strain (one bulk copy each); the padding is never read as data;
+//   [Dp/32][S][32] weights in tiles of 32 consecutive draws x S strains (Dp = D rounded up to 32): the
+//           tile of a Gibbs round is ONE contiguous, 256-byte aligned run of S*256 bytes -- a single bulk
+//           copy -- and inside it the 32 draws of a strain are consecutive (conflict-free lanes); the
+//           padding of the last tile is never read as data;
 //   [D]     normaliser per draw (k_hard);
 //   [D]     the read letter of every draw as an int code (k_gibbs statistics), stored in D double slots.
 __device__ __forceinline__ int padded_draws(int D) { return (D + 31) & ~31; }
 __device__ __forceinline__ double* group_weights(double* W, const StepGroup& g) { return W + g.w_off; }
+__device__ __forceinline__ long long weight_index(int d, int s, int S) { return ((long long)(d >> 5) * S + s) * 32 + (d & 31); }
 __device__ __forceinline__ double* group_norms(double* W, const StepGroup& g)
 {
     return W + g.w_off + (long long)g.S * padded_draws(g.D);
@@ -148,13 +151,12 @@ __global__ void __launch_bounds__(128) k_weights(const StepGroup* __restrict__ g
     const int mate = I[g.draw_off + g.D + d];
     const int rid = I[g.rid_off + r];
     double* w = group_weights(W, g);
-    const int Dp = padded_draws(g.D);
     for (int s = 0; s < g.S; ++s)
     {
         const double* row = g.ll + (long long)I[g.slot_off + s] * g.ll_stride;
         double v = row[rid];
         if (mate >= 0) v += row[mate];
-        w[(long long)s * Dp + d] = exp(v);
+        w[weight_index(d, s, g.S)] = exp(v);
     }
     if (g.mode == MODE_GIBBS)
     {
@@ -180,11 +182,10 @@ __global__ void __launch_bounds__(256) k_hard(const StepGroup* __restrict__ grou
     __syncthreads();
     double* T = group_norms(W, g);
     const double* wt = group_weights(W, g);
-    const int Dp = padded_draws(g.D);
     for (int d = tid; d < g.D; d += blockDim.x)
     {
         double t = 0;
-        for (int s = 0; s < S; ++s) t += ab[s] * wt[(long long)s * Dp + d];
+        for (int s = 0; s < S; ++s) t += ab[s] * wt[weight_index(d, s, S)];
         T[d] = t;
     }
     __syncthreads();
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(256) k_hard(const StepGroup* __restrict__ grou
         const double a_s = ab[s];
         for (int d = lane; d < g.D; d += 32)
         {
-            const double p = a_s * wt[(long long)s * Dp + d] / T[d];
+            const double p = a_s * wt[weight_index(d, s, S)] / T[d];
             acc[0] += p;
             const int r = I[g.draw_off + d];
             const char* rs = g.pool_chars + I[g.rid_off + g.m + r];
@@ -251,13 +252,18 @@ __global__ void __launch_bounds__(256) k_hard(const StepGroup* __restrict__ grou
 // there are fewer than two strains.
 //
 // One warp per subgroup, 32 consecutive draws per round, one draw per lane, evaluated SPECULATIVELY
-// and then corrected to the exact sequential result: lane j computes its draw with the masses as
-// they would be after the draws of lanes < j *as currently guessed* (a ballot per strain gives the
-// prefix counts); the round repeats until no lane changes its answer.  Lane 0 is exact after the
-// first pass, and lane j is exact once lanes < j are, so the fixed point IS the sequential chain;
-// masses move by 1 in thousands, so two passes almost always suffice.  Cumulative sums run in
-// strain order in FP64, like the reference's accumulate/partial_sum.
-__global__ void __launch_bounds__(32) k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I,
+// and then corrected to the exact sequential result.  With m[] the masses at the start of the round,
+// lane j's cumulative weight at strain s is  base_j(s) + corr_j(s):
+//     base_j(s) = sum_{s' <= s} m[s'] * w_j[s']                      (pass 1, once per round)
+//     corr_j(s) = sum_{i < j, pick_i <= s} w_j[pick_i]               (every earlier lane adds 1 to its pick)
+// Pass 1 picks with corr = 0.  Each following pass publishes the picks, and every lane CHECKS its
+// pick against the two cumulative weights around it -- 32 broadcast reads instead of a walk over
+// all S strains -- re-deriving it only when the check fails.  Lane 0 is exact after pass 1 and lane j
+// is exact once lanes < j are, so the fixed point IS the sequential chain; masses move by 1 in
+// thousands, so a round almost always settles in two passes (the counters report it).
+// The weights of a round are S aligned 256-byte rows, bulk-copied (TMA, no tensor map) into a
+// double-buffered shared tile while the previous round is being settled.
+__global__ void __launch_bounds__(32, 1) k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I,
                                               double* __restrict__ Dar, double* __restrict__ W,
                                               const double* __restrict__ U, unsigned long long* counters, int smem_S)
 {
@@ -270,8 +276,9 @@ __global__ void __launch_bounds__(32) k_gibbs(const StepGroup* __restrict__ grou
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(mass + smem_S);  // [2]
     int* cnt = reinterpret_cast<int*>(bars + 2);     // [smem_S][8]
     int* hist = cnt + smem_S * 8;                    // [smem_S]
+    int* picks = hist + smem_S;                      // [32]
     const int lane = threadIdx.x, S = g.S, D = g.D;
-    const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+    const unsigned full = 0xffffffffu;
     const double* wt = group_weights(W, g);
     const int* code = group_codes(W, g);
     const int Dp = padded_draws(D);
@@ -283,48 +290,108 @@ __global__ void __launch_bounds__(32) k_gibbs(const StepGroup* __restrict__ grou
     const int per_sweep = Dp / 32;
     const long long n_rounds = (S >= 2) ? (long long)g.nsweeps * per_sweep : 0;
     unsigned long long rounds = 0, passes = 0;
-    // stage the weights of round r: S rows of 32 consecutive draws, 256 B each, one bulk copy per row
-    auto stage = [&](long long r) {
-        const int b = (int)(r & 1);
-        const int blk = (int)(r % per_sweep);
-        if (lane == 0) mbar_expect_tx(&bars[b], (unsigned)S * 256u);
-        __syncwarp();
-        for (int s = lane; s < S; s += 32)
-            bulk_g2s(wbuf + ((size_t)b * smem_S + s) * 32, wt + (long long)s * Dp + blk * 32, 256u, &bars[b]);
+    // stage the weights of round r: one tile of S x 32 draws, S*256 contiguous bytes, one bulk copy
+    auto stage = [&](long long r, int blk) {
+        if (lane == 0)
+        {
+            const int b = (int)(r & 1);
+            mbar_expect_tx(&bars[b], (unsigned)S * 256u);
+            bulk_g2s(wbuf + (size_t)b * smem_S * 32, wt + (long long)blk * S * 32, (unsigned)S * 256u, &bars[b]);
+        }
     };
-    if (n_rounds > 0) stage(0);
+    if (n_rounds > 0) stage(0, 0);
+    int sweep = 0, blk = 0;
+    int top_step = 1;
+    while (top_step * 2 <= S - 1) top_step *= 2;
     for (long long r = 0; r < n_rounds; ++r)
     {
-        const int sweep = (int)(r / per_sweep), blk = (int)(r % per_sweep);
         const int d = blk * 32 + lane;
         const bool valid = d < D;
         const double u = valid ? U[(long long)sweep * D + d] : 0.0;
         const int cd = (valid && g.mode == MODE_GIBBS) ? code[d] : 0;
-        if (r + 1 < n_rounds) stage(r + 1);  // overlaps this round's arithmetic
+        const int blk_next = (blk + 1 == per_sweep) ? 0 : blk + 1;
+        if (r + 1 < n_rounds) stage(r + 1, blk_next);  // overlaps this round's arithmetic
         mbar_wait(&bars[r & 1], (unsigned)((r >> 1) & 1));
         const double* wl = wbuf + (size_t)(r & 1) * smem_S * 32 + lane;
         double* cl = cumbuf + lane;
-        int c = -1;
+        // ---- pass 1: base cumulative weights, in strain order like std::partial_sum
+        double cum = 0;
+        {
+            int s = 0;
+            for (; s + 8 <= S; s += 8)
+            {
+                double m8[8], w8[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { m8[q] = mass[s + q]; w8[q] = wl[(s + q) * 32]; }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { cum = fma(m8[q], w8[q], cum); cl[(s + q) * 32] = cum; }
+            }
+            for (; s < S; ++s) { cum = fma(mass[s], wl[s * 32], cum); cl[s * 32] = cum; }
+        }
+        const double base_tot = cum;
+        int c;
+        {
+            // lower_bound over the (non-decreasing) cumulative weights of strains 0..S-2; S-1 if none reaches u*total
+            const double thr = u * base_tot;
+            int cn = 0;
+            for (int step = top_step; step > 0; step >>= 1)
+            {
+                const int p = cn + step;
+                if (p <= S - 1 && cl[(p - 1) * 32] < thr) cn = p;
+            }
+            c = valid ? min(cn, S - 1) : -1;
+        }
+        ++passes;
+        // ---- settle: check every pick against the picks of the earlier lanes until nothing moves
         for (;;)
         {
-            double cum = 0;
-#pragma unroll 4
-            for (int s = 0; s < S; ++s)
+            picks[lane] = c;  // the rare re-derivation below reads them from shared memory
+            // gather the earlier picks, then their weights, then add: three independent phases, so the
+            // shuffles and the shared-memory reads overlap instead of forming one long dependent chain
+            int ci[31];
+            double wi[31];
+#pragma unroll
+            for (int i = 0; i < 31; ++i) ci[i] = __shfl_sync(full, c, i);
+#pragma unroll
+            for (int i = 0; i < 31; ++i) wi[i] = wl[max(ci[i], 0) * 32];
+            double le_prev = 0, le_here = 0, tot = 0;  // corr(c-1), corr(c), corr(S-1), each summed in lane order
+#pragma unroll
+            for (int i = 0; i < 31; ++i)
             {
-                const unsigned m = __ballot_sync(full, c == s);
-                const double as = mass[s] + (double)__popc(m & lt);
-                cum = fma(as, wl[s * 32], cum);
-                cl[s * 32] = cum;
+                // a term counts with multiplier 1.0 or 0.0: fma(w, 1, acc) == acc + w and fma(w, 0, acc) == acc
+                const bool live = (i < lane) && (ci[i] >= 0);
+                const double w = wi[i];
+                tot = fma(w, live ? 1.0 : 0.0, tot);
+                le_here = fma(w, (live && ci[i] <= c) ? 1.0 : 0.0, le_here);
+                le_prev = fma(w, (live && ci[i] < c) ? 1.0 : 0.0, le_prev);
             }
-            const double thr = u * cum;
-            int cn = 0;
-#pragma unroll 4
-            for (int s = 0; s < S; ++s) cn += (cl[s * 32] < thr) ? 1 : 0;
-            if (cn > S - 1) cn = S - 1;
-            if (!valid) cn = -1;
-            const bool changed = __any_sync(full, cn != c);
-            c = cn;
+            __syncwarp();
+            bool ok = true;
+            if (valid)
+            {
+                const double thr = u * (base_tot + tot);
+                const bool lo_ok = (c == 0) || (cl[(c - 1) * 32] + le_prev < thr);
+                const bool hi_ok = (c == S - 1) || !(cl[c * 32] + le_here < thr);
+                ok = lo_ok && hi_ok;
+                if (!ok)
+                {   // rare: walk the strains with the same definition of the cumulative weight
+                    int cn = 0;
+                    for (int s = 0; s < S; ++s)
+                    {
+                        double corr = 0;
+                        for (int i = 0; i < lane; ++i)
+                        {
+                            const int ci = picks[i];
+                            if (ci >= 0 && ci <= s) corr += wl[ci * 32];
+                        }
+                        if (cl[s * 32] + corr < thr) ++cn; else break;
+                    }
+                    c = min(cn, S - 1);
+                }
+            }
             ++passes;
+            const bool changed = __any_sync(full, !ok);
+            __syncwarp();
             if (!changed) break;
         }
         ++rounds;
@@ -336,6 +403,8 @@ __global__ void __launch_bounds__(32) k_gibbs(const StepGroup* __restrict__ grou
         __syncwarp();
         for (int s = lane; s < S; s += 32) { mass[s] += (double)hist[s]; hist[s] = 0; }
         __syncwarp();
+        if (blk_next == 0) ++sweep;
+        blk = blk_next;
     }
     if (lane == 0 && counters)
     {
@@ -405,7 +474,7 @@ void launch_level_step(const StepLaunch& L, cudaStream_t st, int* launches)
     {
         if (L.gibbs_begin) RAMBL_CUDA(cudaEventRecord(L.gibbs_begin, st));
         const int smem_S = (L.max_S + 3) & ~3;
-        const size_t smem = sizeof(double) * ((size_t)smem_S * 97 + 2) + sizeof(int) * ((size_t)smem_S * 9);
+        const size_t smem = sizeof(double) * ((size_t)smem_S * 97 + 2) + sizeof(int) * ((size_t)smem_S * 9 + 32);
         static size_t configured = 0;
         if (smem > configured)
         {
