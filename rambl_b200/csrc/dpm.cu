@@ -251,48 +251,59 @@ __global__ void __launch_bounds__(256) k_hard(const StepGroup* __restrict__ grou
 // std::mt19937(1234) stream the reference restarts on every call, and no random number at all when
 // there are fewer than two strains.
 //
-// One warp per subgroup, 32 consecutive draws per round, one draw per lane, evaluated SPECULATIVELY
-// and then corrected to the exact sequential result.  With m[] the masses at the start of the round,
-// lane j's cumulative weight at strain s is  base_j(s) + corr_j(s):
+// One CTA of GIBBS_NW warps per subgroup, 32 consecutive draws per round, draw j on lane j of EVERY
+// warp, evaluated SPECULATIVELY and then corrected to the exact sequential result.  With m[] the masses
+// at the start of the round, lane j's cumulative weight at strain s is  base_j(s) + corr_j(s):
 //     base_j(s) = sum_{s' <= s} m[s'] * w_j[s']                      (pass 1, once per round)
 //     corr_j(s) = sum_{i < j, pick_i <= s} w_j[pick_i]               (every earlier lane adds 1 to its pick)
-// Pass 1 picks with corr = 0.  Each following pass publishes the picks, and every lane CHECKS its
-// pick against the two cumulative weights around it -- 32 broadcast reads instead of a walk over
+// Pass 1 picks with corr = 0 (binary search of u * total).  Each following pass lets every lane CHECK
+// its pick against the two cumulative weights around it -- 31 gathered weights instead of a walk over
 // all S strains -- re-deriving it only when the check fails.  Lane 0 is exact after pass 1 and lane j
 // is exact once lanes < j are, so the fixed point IS the sequential chain; masses move by 1 in
 // thousands, so a round almost always settles in two passes (the counters report it).
-// The weights of a round are S aligned 256-byte rows, bulk-copied (TMA, no tensor map) into a
+// The warps split the two long loops of a round -- warp q owns strain chunk q of the prefix sums
+// and source-lane chunk q of the gather -- and exchange partial sums through shared memory; all
+// warps then hold identical picks, so the cheap steps are simply done by each of them.  The sums are
+// therefore defined chunk-wise: base(s) = off[chunk] + (fma chain inside the chunk), corr = p0+p1+..,
+// each p in lane order; the same definition serves the check and the re-derivation, and every
+// cumulative weight stays non-decreasing in s.
+// The weights of a round are one contiguous S x 32 tile, bulk-copied (TMA, no tensor map) into a
 // double-buffered shared tile while the previous round is being settled.
-__global__ void __launch_bounds__(32, 1) k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I,
-                                              double* __restrict__ Dar, double* __restrict__ W,
-                                              const double* __restrict__ U, unsigned long long* counters, int smem_S)
+constexpr int GIBBS_NW = 4;
+constexpr int GIBBS_L = 32 / GIBBS_NW;  // source lanes per warp in the gather
+
+__global__ void __launch_bounds__(32 * GIBBS_NW, 1)
+k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double* __restrict__ Dar,
+        double* __restrict__ W, const double* __restrict__ U, unsigned long long* counters, int smem_S)
 {
     const StepGroup g = groups[blockIdx.x];
     if (g.mode != MODE_GIBBS && g.mode != MODE_ASSIGN) return;
     extern __shared__ __align__(128) double gibbs_smem[];  // sized for the largest S of the launch (smem_S)
     double* wbuf = gibbs_smem;                       // [2][strain][lane] weights of a round's 32 draws (bulk-copied)
-    double* cumbuf = wbuf + 2 * smem_S * 32;         // [strain][lane] cumulative weights
+    double* cumbuf = wbuf + 2 * smem_S * 32;         // [strain][lane] prefix sums inside the strain chunk
     double* mass = cumbuf + smem_S * 32;             // [smem_S]
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(mass + smem_S);  // [2]
+    double* ctot = mass + smem_S;                    // [GIBBS_NW][lane] chunk totals
+    double* part = ctot + GIBBS_NW * 32;             // [2][3][GIBBS_NW][lane] partial gather sums, double-buffered by pass
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(part + 2 * 3 * GIBBS_NW * 32);  // [2]
     int* cnt = reinterpret_cast<int*>(bars + 2);     // [smem_S][8]
     int* hist = cnt + smem_S * 8;                    // [smem_S]
     int* picks = hist + smem_S;                      // [32]
-    const int lane = threadIdx.x, S = g.S, D = g.D;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, S = g.S, D = g.D;
     const unsigned full = 0xffffffffu;
     const double* wt = group_weights(W, g);
     const int* code = group_codes(W, g);
     const int Dp = padded_draws(D);
-    for (int k = lane; k < S * 8; k += 32) cnt[k] = 0;
-    for (int s = lane; s < S; s += 32) { mass[s] = Dar[g.ab_off + s]; hist[s] = 0; }
-    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    for (int k = tid; k < S * 8; k += blockDim.x) cnt[k] = 0;
+    for (int s = tid; s < S; s += blockDim.x) { mass[s] = Dar[g.ab_off + s]; hist[s] = 0; }
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncwarp();
+    __syncthreads();
     const int per_sweep = Dp / 32;
     const long long n_rounds = (S >= 2) ? (long long)g.nsweeps * per_sweep : 0;
     unsigned long long rounds = 0, passes = 0;
     // stage the weights of round r: one tile of S x 32 draws, S*256 contiguous bytes, one bulk copy
     auto stage = [&](long long r, int blk) {
-        if (lane == 0)
+        if (tid == 0)
         {
             const int b = (int)(r & 1);
             mbar_expect_tx(&bars[b], (unsigned)S * 256u);
@@ -303,32 +314,58 @@ __global__ void __launch_bounds__(32, 1) k_gibbs(const StepGroup* __restrict__ g
     int sweep = 0, blk = 0;
     int top_step = 1;
     while (top_step * 2 <= S - 1) top_step *= 2;
+    const int Cs = (S + GIBBS_NW - 1) / GIBBS_NW;               // strains per chunk
+    const int s_lo = min(S, warp * Cs), s_hi = min(S, s_lo + Cs);  // this warp's chunk
+    unsigned pass_id = 0;
+    // the uniform and the read letter of a draw come from global memory: fetch them one round ahead
+    double u_next = (n_rounds > 0 && lane < D) ? U[lane] : 0.0;
+    int cd_next = (n_rounds > 0 && lane < D && g.mode == MODE_GIBBS) ? code[lane] : 0;
     for (long long r = 0; r < n_rounds; ++r)
     {
         const int d = blk * 32 + lane;
         const bool valid = d < D;
-        const double u = valid ? U[(long long)sweep * D + d] : 0.0;
-        const int cd = (valid && g.mode == MODE_GIBBS) ? code[d] : 0;
+        const double u = u_next;
+        const int cd = cd_next;
         const int blk_next = (blk + 1 == per_sweep) ? 0 : blk + 1;
-        if (r + 1 < n_rounds) stage(r + 1, blk_next);  // overlaps this round's arithmetic
+        if (r + 1 < n_rounds)
+        {
+            stage(r + 1, blk_next);  // overlaps this round's arithmetic
+            const int dn = blk_next * 32 + lane;
+            const int sweep_n = sweep + (blk_next == 0 ? 1 : 0);
+            u_next = (dn < D) ? U[(long long)sweep_n * D + dn] : 0.0;
+            cd_next = (dn < D && g.mode == MODE_GIBBS) ? code[dn] : 0;
+        }
         mbar_wait(&bars[r & 1], (unsigned)((r >> 1) & 1));
         const double* wl = wbuf + (size_t)(r & 1) * smem_S * 32 + lane;
         double* cl = cumbuf + lane;
-        // ---- pass 1: base cumulative weights, in strain order like std::partial_sum
-        double cum = 0;
+        // ---- pass 1: prefix sums of mass * weight over this warp's strain chunk, in strain order
         {
-            int s = 0;
-            for (; s + 8 <= S; s += 8)
+            double cum = 0;
+            int s = s_lo;
+            for (; s + 4 <= s_hi; s += 4)
             {
-                double m8[8], w8[8];
+                double m4[4], w4[4];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { m8[q] = mass[s + q]; w8[q] = wl[(s + q) * 32]; }
+                for (int q = 0; q < 4; ++q) { m4[q] = mass[s + q]; w4[q] = wl[(s + q) * 32]; }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { cum = fma(m8[q], w8[q], cum); cl[(s + q) * 32] = cum; }
+                for (int q = 0; q < 4; ++q) { cum = fma(m4[q], w4[q], cum); cl[(s + q) * 32] = cum; }
             }
-            for (; s < S; ++s) { cum = fma(mass[s], wl[s * 32], cum); cl[s * 32] = cum; }
+            for (; s < s_hi; ++s) { cum = fma(mass[s], wl[s * 32], cum); cl[s * 32] = cum; }
+            ctot[warp * 32 + lane] = cum;
         }
-        const double base_tot = cum;
+        __syncthreads();
+        double off[GIBBS_NW + 1];
+        off[0] = 0;
+#pragma unroll
+        for (int q = 0; q < GIBBS_NW; ++q) off[q + 1] = off[q] + ctot[q * 32 + lane];
+        const double base_tot = off[GIBBS_NW];
+        // base(s) = offset of the chunk of s + prefix sum inside the chunk
+        auto base = [&](int s) {
+            double o = 0;
+#pragma unroll
+            for (int q = 1; q < GIBBS_NW; ++q) o = (s >= q * Cs) ? off[q] : o;
+            return o + cl[s * 32];
+        };
         int c;
         {
             // lower_bound over the (non-decreasing) cumulative weights of strains 0..S-2; S-1 if none reaches u*total
@@ -337,80 +374,102 @@ __global__ void __launch_bounds__(32, 1) k_gibbs(const StepGroup* __restrict__ g
             for (int step = top_step; step > 0; step >>= 1)
             {
                 const int p = cn + step;
-                if (p <= S - 1 && cl[(p - 1) * 32] < thr) cn = p;
+                if (p <= S - 1 && base(p - 1) < thr) cn = p;
             }
-            c = valid ? min(cn, S - 1) : -1;
+            c = valid ? cn : -1;
         }
         ++passes;
         // ---- settle: check every pick against the picks of the earlier lanes until nothing moves
         for (;;)
         {
-            picks[lane] = c;  // the rare re-derivation below reads them from shared memory
-            // gather the earlier picks, then their weights, then add: three independent phases, so the
-            // shuffles and the shared-memory reads overlap instead of forming one long dependent chain
-            int ci[31];
-            double wi[31];
-#pragma unroll
-            for (int i = 0; i < 31; ++i) ci[i] = __shfl_sync(full, c, i);
-#pragma unroll
-            for (int i = 0; i < 31; ++i) wi[i] = wl[max(ci[i], 0) * 32];
-            double le_prev = 0, le_here = 0, tot = 0;  // corr(c-1), corr(c), corr(S-1), each summed in lane order
-#pragma unroll
-            for (int i = 0; i < 31; ++i)
+            double* pbuf = part + (size_t)(pass_id & 1) * 3 * GIBBS_NW * 32;
+            ++pass_id;
+            if (warp == 0) picks[lane] = c;  // the rare re-derivation below reads them from shared memory
             {
-                // a term counts with multiplier 1.0 or 0.0: fma(w, 1, acc) == acc + w and fma(w, 0, acc) == acc
-                const bool live = (i < lane) && (ci[i] >= 0);
-                const double w = wi[i];
-                tot = fma(w, live ? 1.0 : 0.0, tot);
-                le_here = fma(w, (live && ci[i] <= c) ? 1.0 : 0.0, le_here);
-                le_prev = fma(w, (live && ci[i] < c) ? 1.0 : 0.0, le_prev);
+                // this warp gathers source lanes [warp*L, warp*L + L): picks, then weights, then sums
+                int ci[GIBBS_L];
+                double wi[GIBBS_L];
+#pragma unroll
+                for (int i = 0; i < GIBBS_L; ++i) ci[i] = __shfl_sync(full, c, warp * GIBBS_L + i);
+#pragma unroll
+                for (int i = 0; i < GIBBS_L; ++i) wi[i] = wl[max(ci[i], 0) * 32];
+                double p_prev = 0, p_here = 0, p_tot = 0;
+#pragma unroll
+                for (int i = 0; i < GIBBS_L; ++i)
+                {
+                    // a term counts with multiplier 1.0 or 0.0: fma(w, 1, acc) == acc + w and fma(w, 0, acc) == acc
+                    const bool live = (warp * GIBBS_L + i < lane) && (ci[i] >= 0);
+                    p_tot = fma(wi[i], live ? 1.0 : 0.0, p_tot);
+                    p_here = fma(wi[i], (live && ci[i] <= c) ? 1.0 : 0.0, p_here);
+                    p_prev = fma(wi[i], (live && ci[i] < c) ? 1.0 : 0.0, p_prev);
+                }
+                pbuf[(0 * GIBBS_NW + warp) * 32 + lane] = p_tot;
+                pbuf[(1 * GIBBS_NW + warp) * 32 + lane] = p_here;
+                pbuf[(2 * GIBBS_NW + warp) * 32 + lane] = p_prev;
             }
-            __syncwarp();
+            __syncthreads();
+            double tot = 0, le_here = 0, le_prev = 0;  // corr(S-1), corr(c), corr(c-1): chunk partials added in order
+#pragma unroll
+            for (int q = 0; q < GIBBS_NW; ++q)
+            {
+                tot += pbuf[(0 * GIBBS_NW + q) * 32 + lane];
+                le_here += pbuf[(1 * GIBBS_NW + q) * 32 + lane];
+                le_prev += pbuf[(2 * GIBBS_NW + q) * 32 + lane];
+            }
             bool ok = true;
             if (valid)
             {
                 const double thr = u * (base_tot + tot);
-                const bool lo_ok = (c == 0) || (cl[(c - 1) * 32] + le_prev < thr);
-                const bool hi_ok = (c == S - 1) || !(cl[c * 32] + le_here < thr);
+                const bool lo_ok = (c == 0) || (base(c - 1) + le_prev < thr);
+                const bool hi_ok = (c == S - 1) || !(base(c) + le_here < thr);
                 ok = lo_ok && hi_ok;
                 if (!ok)
                 {   // rare: walk the strains with the same definition of the cumulative weight
                     int cn = 0;
-                    for (int s = 0; s < S; ++s)
+                    for (int s = 0; s < S - 1; ++s)
                     {
                         double corr = 0;
-                        for (int i = 0; i < lane; ++i)
+                        for (int q = 0; q < GIBBS_NW; ++q)
                         {
-                            const int ci = picks[i];
-                            if (ci >= 0 && ci <= s) corr += wl[ci * 32];
+                            double p = 0;
+                            for (int i = q * GIBBS_L; i < (q + 1) * GIBBS_L && i < lane; ++i)
+                            {
+                                const int ci = picks[i];
+                                if (ci >= 0 && ci <= s) p += wl[ci * 32];
+                            }
+                            corr += p;
                         }
-                        if (cl[s * 32] + corr < thr) ++cn; else break;
+                        if (base(s) + corr < thr) ++cn; else break;
                     }
-                    c = min(cn, S - 1);
+                    c = cn;
                 }
             }
             ++passes;
-            const bool changed = __any_sync(full, !ok);
-            __syncwarp();
-            if (!changed) break;
+            // every warp holds the same picks and reaches the same verdict
+            if (!__any_sync(full, !ok)) break;
+            __syncthreads();  // picks[] is rewritten by the next pass
         }
         ++rounds;
-        if (valid)
+        if (warp == 0)
         {
-            atomicAdd(&hist[c], 1);
-            if (g.mode == MODE_GIBBS) atomicAdd(&cnt[c * 8 + cd], 1);
+            if (valid)
+            {
+                atomicAdd(&hist[c], 1);
+                if (g.mode == MODE_GIBBS) atomicAdd(&cnt[c * 8 + cd], 1);
+            }
+            __syncwarp();
+            for (int s = lane; s < S; s += 32) { mass[s] += (double)hist[s]; hist[s] = 0; }
         }
-        __syncwarp();
-        for (int s = lane; s < S; s += 32) { mass[s] += (double)hist[s]; hist[s] = 0; }
-        __syncwarp();
+        __syncthreads();
         if (blk_next == 0) ++sweep;
         blk = blk_next;
     }
-    if (lane == 0 && counters)
+    if (tid == 0 && counters)
     {
         atomicAdd(&counters[0], rounds);
         atomicAdd(&counters[1], passes);
     }
+    if (warp != 0) return;
     // normalise the masses; fold the averaged counts into the models (lines 217-243)
     double z = 0;
     for (int s = 0; s < S; ++s) z += mass[s];
@@ -474,14 +533,14 @@ void launch_level_step(const StepLaunch& L, cudaStream_t st, int* launches)
     {
         if (L.gibbs_begin) RAMBL_CUDA(cudaEventRecord(L.gibbs_begin, st));
         const int smem_S = (L.max_S + 3) & ~3;
-        const size_t smem = sizeof(double) * ((size_t)smem_S * 97 + 2) + sizeof(int) * ((size_t)smem_S * 9 + 32);
+        const size_t smem = sizeof(double) * ((size_t)smem_S * 97 + 4 * 32 + 2 * 3 * 4 * 32 + 2) + sizeof(int) * ((size_t)smem_S * 9 + 32);
         static size_t configured = 0;
         if (smem > configured)
         {
             RAMBL_CUDA(cudaFuncSetAttribute(k_gibbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = smem;
         }
-        k_gibbs<<<L.n_groups, 32, smem, st>>>(L.groups, L.iarena, L.darena, L.weights, L.uniforms, L.counters, smem_S);
+        k_gibbs<<<L.n_groups, 128, smem, st>>>(L.groups, L.iarena, L.darena, L.weights, L.uniforms, L.counters, smem_S);
         if (L.gibbs_end) RAMBL_CUDA(cudaEventRecord(L.gibbs_end, st));
         ++*launches;
     }
