@@ -5,6 +5,8 @@
 #include <cstring>
 #include <memory>
 #include <sstream>
+#include <thread>
+#include <atomic>
 
 #include "engine.hpp"
 #include "msa_sp.hpp"
@@ -76,28 +78,80 @@ struct rambl_batch
 
 namespace {
 
+// run fn(i) for i in [lo, hi) on the host cores (subgroups are independent); the first error wins
+template <typename F>
+void parallel_for(size_t lo, size_t hi, F&& fn)
+{
+    const size_t n = hi > lo ? hi - lo : 0;
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    nt = (unsigned)std::min<size_t>(std::min<size_t>(nt, 64), n);
+    if (nt <= 1)
+    {
+        for (size_t i = lo; i < hi; ++i) fn(i);
+        return;
+    }
+    std::atomic<size_t> next(lo);
+    std::atomic<bool> failed(false);
+    std::string what;
+    int code = RAMBL_OK;
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; ++t)
+        pool.emplace_back([&] {
+            for (;;)
+            {
+                const size_t i = next.fetch_add(1);
+                if (i >= hi || failed.load()) return;
+                try { fn(i); }
+                catch (const Error& e)
+                {
+                    if (!failed.exchange(true)) { what = e.what(); code = e.code; }
+                }
+                catch (const std::exception& e)
+                {
+                    if (!failed.exchange(true)) { what = e.what(); code = RAMBL_ERR_INVALID; }
+                }
+            }
+        });
+    for (auto& t : pool) t.join();
+    if (failed.load()) throw Error(code, what);
+}
+
+// phase A for the subgroups added since the last call; every subgroup lists its alignment problems
+// privately, the lists are then appended to the batch in subgroup order
 void thread_pending(rambl_batch* b)
 {
-    for (size_t i = b->threaded_upto; i < b->subs.size(); ++i)
-    {
+    const size_t lo = b->threaded_upto, hi = b->subs.size();
+    std::vector<MsaBatch> local(hi - lo);
+    parallel_for(lo, hi, [&](size_t i) {
         Subgroup& s = *b->subs[i];
         s.builder.reset(new GraphBuilder);
-        s.builder->thread(s.gene, s.reads, b->msa);
+        s.builder->thread(s.gene, s.reads, local[i - lo]);
+    });
+    for (size_t i = lo; i < hi; ++i)
+    {
+        const MsaBatch& m = local[i - lo];
+        b->subs[i]->builder->rebase_problems(b->msa.problems());
+        for (int p = 0; p < m.problems(); ++p)
+        {
+            for (int q = m.prob_seq_off[p]; q < m.prob_seq_off[p + 1]; ++q)
+                b->msa.add_sequence(m.chars.data() + m.seq_off[q], m.seq_off[q + 1] - m.seq_off[q]);
+            b->msa.end_problem();
+        }
     }
-    b->threaded_upto = b->subs.size();
+    b->threaded_upto = hi;
 }
 
 void finish_pending(rambl_batch* b, const MsaResult& rows)
 {
-    for (auto& sp : b->subs)
-    {
-        Subgroup& s = *sp;
-        if (s.built || !s.builder) continue;
+    parallel_for(0, b->subs.size(), [&](size_t i) {
+        Subgroup& s = *b->subs[i];
+        if (s.built || !s.builder) return;
         s.builder->finish(rows, s.graph);
         s.builder.reset();
         s.input.graph = &s.graph;
         s.built = true;
-    }
+    });
     b->msa = MsaBatch();
 }
 

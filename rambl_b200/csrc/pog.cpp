@@ -650,6 +650,12 @@ struct GraphBuilder::Impl
 GraphBuilder::GraphBuilder() : m(new Impl) {}
 GraphBuilder::~GraphBuilder() { delete m; }
 int GraphBuilder::n_problems() const { return m->n_problems; }
+void GraphBuilder::rebase_problems(int first)
+{
+    const int shift = first - m->first_problem;
+    for (LevelPlan& lp : m->plans) if (lp.problem >= 0) lp.problem += shift;
+    m->first_problem = first;
+}
 
 void GraphBuilder::thread(const std::string& gene, const std::vector<AlignedRead>& reads, MsaBatch& batch)
 {

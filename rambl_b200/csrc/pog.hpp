@@ -69,6 +69,8 @@ public:
     // phase C; `rows` holds the solved problems of the batch that thread() appended to
     void finish(const MsaResult& rows, FlatGraph& out);
     int n_problems() const;
+    // the problems thread() listed start at index `first` of the batch that finish() will be given
+    void rebase_problems(int first);
 
 private:
     struct Impl;

@@ -198,15 +198,14 @@ def _emit_read(strain: StrainTruth, start: int, length: int, rng: np.random.Gene
     return int(gp[start]), cigar, "".join(bases)
 
 
-def make_subgroup(n_reads: int = 2000, read_len: int = 100, n_strains: int = 3, divergence=(0.01, 0.03),
+def simulate_raw_reads(n_reads: int = 2000, read_len: int = 100, n_strains: int = 3, divergence=(0.01, 0.03),
                   sub_err: float = 0.005, indel_err: float = 0.0, indel_frac: float = 0.1,
                   homopolymer_bias: bool = False, paired: bool = False, max_depth: int = 800,
                   gene: Optional[str] = None, window: Optional[Tuple[int, int]] = None, seed: int = 0,
-                  max_ins: int = 10, abundances: Optional[Sequence[float]] = None) -> Subgroup:
-    """Simulate one taxonomic subgroup (a seed gene window and the reads mapped to it).
-
-    ``window`` is a 0-based half-open slice of the gene (default: the whole gene, the way
-    scripts/rambl.py:181-187 runs StrainCall with ``-w 5000``)."""
+                  max_ins: int = 10, abundances: Optional[Sequence[float]] = None) -> Tuple[str, List[Tuple[str, int, str, str]], List[StrainTruth]]:
+    """Simulate the raw mapped reads of one subgroup: (gene window, [(name, pos, cigar, seq)], strains).
+    Reads are in sequencing order; names of mates end in /1 and /2 (the suffix StrainCall derives from the
+    SAM flag, StrainCall.cpp:552-562).  max_depth and abundances are accepted for a uniform signature."""
     rng = np.random.default_rng(seed)
     gene = ecoli_16s() if gene is None else gene
     if window is not None:
@@ -248,6 +247,22 @@ def make_subgroup(n_reads: int = 2000, read_len: int = 100, n_strains: int = 3, 
                 raw.append((f"s{rid:07d}",) + r)
             rid += 1
 
+    return gene, raw, strains
+
+
+def make_subgroup(n_reads: int = 2000, read_len: int = 100, n_strains: int = 3, divergence=(0.01, 0.03),
+                  sub_err: float = 0.005, indel_err: float = 0.0, indel_frac: float = 0.1,
+                  homopolymer_bias: bool = False, paired: bool = False, max_depth: int = 800,
+                  gene: Optional[str] = None, window: Optional[Tuple[int, int]] = None, seed: int = 0,
+                  max_ins: int = 10, abundances: Optional[Sequence[float]] = None) -> Subgroup:
+    """Simulate one taxonomic subgroup (a seed gene window and the reads mapped to it), in the form
+    StrainCall holds it after load_mapping_reads.
+
+    ``window`` is a 0-based half-open slice of the gene (default: the whole gene, the way
+    scripts/rambl.py:181-187 runs StrainCall with ``-w 5000``)."""
+    gene, raw, strains = simulate_raw_reads(n_reads, read_len, n_strains, divergence, sub_err, indel_err, indel_frac,
+                                            homopolymer_bias, paired, max_depth, gene, window, seed, max_ins, abundances)
+    L = len(gene)
     # ---- depth down-sampling, StrainCall.cpp:505-529,586-592 (window = whole gene here)
     depth = 0
     for (_, p, cg, _s) in raw:
@@ -293,6 +308,34 @@ def make_subgroup(n_reads: int = 2000, read_len: int = 100, n_strains: int = 3, 
         off[i + 1] = off[i] + len(pl)
     val = np.asarray([m for pl in pairs for m in pl], dtype=np.int32)
     return Subgroup(gene, pos, cigar, seq, cn, off, val, len(raw), strains)
+
+
+def write_cli_fixture(dirname: str, gene_name: str, gene: str, raw) -> Tuple[str, str]:
+    """Write what the StrainCall CLI reads: <dir>/genes.fa (+ .fai) and <dir>/reads.sam -- SAM text records
+    sorted by position, standing in for the BAM (tests/samtools_shim/samtools serves them).
+    Returns (fasta path, sam path)."""
+    os.makedirs(dirname, exist_ok=True)
+    fa = os.path.join(dirname, "genes.fa")
+    with open(fa, "w") as f:
+        f.write(">%s\n" % gene_name)
+        for i in range(0, len(gene), 60):
+            f.write(gene[i:i + 60] + "\n")
+    with open(fa + ".fai", "w") as f:
+        f.write("%s\t%d\t%d\t60\t61\n" % (gene_name, len(gene), len(gene_name) + 2))
+    sam = os.path.join(dirname, "reads.sam")
+    recs = []
+    for (nm, p, cg, sq) in raw:
+        flag, base = 0, nm
+        if nm.endswith("/1"):
+            flag, base = 65, nm[:-2]
+        elif nm.endswith("/2"):
+            flag, base = 129, nm[:-2]
+        recs.append((p, "%s\t%d\t%s\t%d\t30\t%s\t*\t0\t0\t%s\t%s" % (base, flag, gene_name, p + 1, cg, sq, "I" * len(sq))))
+    recs.sort(key=lambda r: r[0])
+    with open(sam, "w") as f:
+        for _, line in recs:
+            f.write(line + "\n")
+    return fa, sam
 
 
 # Named workloads of BASELINE.json["configs"] ------------------------------------------------

@@ -1,0 +1,103 @@
+"""The StrainCall drop-in command line (rambl_b200/StrainCall) against the reference CLI built from the
+unmodified sources (oracle/_ref/StrainCall), both reading the same fixtures through tests/samtools_shim."""
+import os
+import subprocess
+
+import pytest
+
+from rambl_b200 import api, synth
+
+from helpers import ROOT
+
+CLI = os.path.join(ROOT, "rambl_b200", "StrainCall")
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "StrainCall")
+SHIM = os.path.join(ROOT, "tests", "samtools_shim")
+
+
+def run_cli(binary, args, cwd):
+    env = dict(os.environ)
+    env["PATH"] = SHIM + os.pathsep + env.get("PATH", "")
+    r = subprocess.run([binary] + args, cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       timeout=600)
+    return r.returncode, r.stdout, r.stderr
+
+
+def test_cli_prints_the_reference_usage():
+    code, out, err = run_cli(CLI, ["-h"], ROOT)
+    assert code == 0 and "StrainCall marker_gene read_mapping" in err and "--max-depth" in err
+
+
+def test_samtools_shim_roundtrip(tmp_path):
+    gene, raw, _ = synth.simulate_raw_reads(50, 40, 2, seed=3, window=(0, 120), indel_err=0.02)
+    fa, sam = synth.write_cli_fixture(str(tmp_path), "g1", gene, raw)
+    code, out, _ = run_cli(os.path.join(SHIM, "samtools"), ["faidx", fa, "g1:11-30"], str(tmp_path))
+    assert code == 0 and "".join(out.split("\n")[1:]) == gene[10:30]
+    code, out, _ = run_cli(os.path.join(SHIM, "samtools"), ["view", sam, "-q", "3", "-F", "1804", "g1:1-120"], str(tmp_path))
+    assert len(out.strip().split("\n")) == len(raw)
+    code, out, _ = run_cli(os.path.join(SHIM, "samtools"), ["mpileup", "-q", "3", "-Q0", "-A", "-r", "g1:1-120", sam], str(tmp_path))
+    assert out.count("\n") > 50
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("spec", [
+    dict(n_reads=150, read_len=50, n_strains=2, seed=21, window=(200, 330), sub_err=0.004, divergence=(0.03, 0.06)),
+    dict(n_reads=200, read_len=60, n_strains=3, seed=22, window=(600, 760), sub_err=0.003, indel_err=0.01,
+         homopolymer_bias=True, divergence=(0.03, 0.07)),
+    dict(n_reads=160, read_len=40, n_strains=2, seed=23, window=(900, 1010), sub_err=0.003, paired=True,
+         divergence=(0.03, 0.06)),
+])
+def test_cli_matches_reference_cli(tmp_path, spec):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/StrainCall not built")
+    gene, raw, _ = synth.simulate_raw_reads(**spec)
+    fa, sam = synth.write_cli_fixture(str(tmp_path), "gene7", gene, raw)
+    args = ["-r", "gene7:1-%d" % len(gene), "-q", "0", "-D", "800", "-I", "13", "-l", "20", "-t", "0.02", "-d", "0.02",
+            "-w", "5000", fa, sam]  # the option set scripts/rambl.py passes (rambl.py:181-187)
+    code_r, out_r, err_r = run_cli(REF_CLI, args, str(tmp_path))
+    code, out, err = run_cli(CLI, args, str(tmp_path))
+    assert code == 0, err
+    if code_r != 0:
+        pytest.skip("the reference CLI crashed on this input (all strains pruned)")
+    assert out == out_r
+    assert out.startswith(">contiggene71")
+    # -G: the graph text
+    code_r, out_r, _ = run_cli(REF_CLI, args + ["-G"], str(tmp_path))
+    code, out, err = run_cli(CLI, args + ["-G"], str(tmp_path))
+    assert code == 0 and out == out_r
+    assert os.listdir(str(tmp_path)).count("genes.fa") == 1 and len(os.listdir(str(tmp_path))) == 3  # temp files removed
+
+
+@pytest.mark.gpu
+def test_cli_windows_match_reference_cli(tmp_path):
+    """Several overlapping scan windows (-w/-o): cropping of reads at window borders, window adjustment."""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/StrainCall not built")
+    gene, raw, _ = synth.simulate_raw_reads(400, 60, 2, seed=31, window=(100, 400), sub_err=0.003, indel_err=0.01,
+                                            divergence=(0.03, 0.06))
+    fa, sam = synth.write_cli_fixture(str(tmp_path), "w1", gene, raw)
+    args = ["-w", "120", "-o", "40", "-l", "30", "-q", "0", fa, sam]
+    code_r, out_r, err_r = run_cli(REF_CLI, args + ["-G"], str(tmp_path))
+    code, out, err = run_cli(CLI, args + ["-G"], str(tmp_path))
+    assert code == 0, err
+    assert code_r == 0
+    assert out == out_r
+    code_r, out_r, err_r = run_cli(REF_CLI, args, str(tmp_path))
+    code, out, err = run_cli(CLI, args, str(tmp_path))
+    assert code == 0, err
+    if code_r == 0:
+        assert out == out_r
+
+
+@pytest.mark.gpu
+def test_cli_equals_library_path(tmp_path):
+    spec = dict(n_reads=300, read_len=100, n_strains=3, seed=5, window=(0, 400), sub_err=0.004, divergence=(0.02, 0.05))
+    gene, raw, _ = synth.simulate_raw_reads(**spec)
+    fa, sam = synth.write_cli_fixture(str(tmp_path), "gx", gene, raw)
+    code, out, err = run_cli(CLI, ["-r", "gx:1-%d" % len(gene), "-w", "5000", "-q", "0", fa, sam], str(tmp_path))
+    assert code == 0, err
+    sg = synth.make_subgroup(**spec)
+    b = api.StrainCallBatch()
+    b.add(sg)
+    b.build_graphs()
+    b.infer()
+    assert out == b.fasta(0, "gx", 1, len(gene), 0.02)
