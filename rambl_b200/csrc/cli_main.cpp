@@ -40,6 +40,7 @@ struct Options  // sc_parameter, StrainCall.cpp:58-95
     float tau = 0.02f, diff_rate = 0.01f;
     int max_depth = 800;
     bool plot_graph = false;
+    std::string dump_inputs;  // --dump-inputs FILE: write what would be handed to the device, then exit
 };
 
 void usage()
@@ -90,6 +91,7 @@ Options parse(int argc, char** argv)
             else if (is_opt(a, "-D", "max-depth")) o.max_depth = std::stoi(next());
             else if (is_opt(a, "-I", "max-ins")) o.max_ins = std::stoi(next());
             else if (is_opt(a, "-G", "plot-graph")) o.plot_graph = true;
+            else if (a == "--dump-inputs") o.dump_inputs = next();
         }
         else
         {
@@ -442,12 +444,31 @@ int main(int argc, char** argv)
         usage();
         return 0;
     }
-    if (rambl_device_count() < 1)
+    if (o.dump_inputs.empty() && rambl_device_count() < 1)
     {
         std::cerr << "StrainCall (rambl_b200): no CUDA device; this build has no CPU path" << std::endl;
         return 2;
     }
     const std::vector<Window> windows = scan_windows(o);
+    if (!o.dump_inputs.empty())
+    {   // host-only: the windows and the reads exactly as they would enter the graph construction
+        std::ofstream out(o.dump_inputs);
+        for (const Window& w : windows)
+        {
+            const std::string roi = w.gn + ":" + std::to_string(w.p0) + "-" + std::to_string(w.p1);
+            WindowReads wr;
+            wr.gene = fetch_sequence(o.gene_file, roi);
+            load_reads(o, roi, wr);
+            out << "WINDOW " << w.gn << " " << w.p0 << " " << w.p1 << " " << wr.pos.size() << "\nGENE " << wr.gene << "\n";
+            for (size_t i = 0; i < wr.pos.size(); ++i)
+            {
+                out << "READ " << wr.pos[i] << " " << wr.cigar[i] << " " << wr.seq[i] << " " << wr.cn[i];
+                for (int k = wr.pair_off[i]; k < wr.pair_off[i + 1]; ++k) out << " " << wr.pair_val[k];
+                out << "\n";
+            }
+        }
+        return 0;
+    }
     rambl_batch* b = rambl_batch_create();
     std::vector<Window> kept;
     for (const Window& w : windows)

@@ -466,6 +466,13 @@ struct Engine
         s.epoch += 1;
         s.levels += 1;
         if (s.cur.empty()) s.done = true;
+        else if (s.levels > g.n_nodes + 1)
+        {   // the level walk of a DAG ends within n_nodes levels; anything longer is a malformed graph
+            s.status = RAMBL_ERR_INVALID;
+            s.have_result = false;
+            s.failed = true;
+            s.done = true;
+        }
     }
 
     void flush_inherits()

@@ -231,7 +231,7 @@ def simulate_raw_reads(n_reads: int = 2000, read_len: int = 100, n_strains: int 
         st = strains[int(which[rid])]
         if paired and rid + 1 < n_reads:
             frag = int(rng.integers(read_len + 20, max(read_len + 21, min(3 * read_len, len(st.seq)))))
-            a = int(rng.integers(0, max(1, len(st.seq) - frag)))
+            a = int(rng.integers(0, max(1, len(st.seq) - frag + 1)))
             r1 = _emit_read(st, a, read_len, rng, sub_err, indel_err, max_ins)
             r2 = _emit_read(st, max(a, a + frag - read_len), read_len, rng, sub_err, indel_err, max_ins)
             nm = f"r{rid // 2:07d}"
@@ -278,6 +278,8 @@ def make_subgroup(n_reads: int = 2000, read_len: int = 100, n_strains: int = 3, 
         depth += ref_len
     depth //= max(L, 1)
     rho = min(1.0, max_depth / (depth + 0.0)) if depth > 0 else 1.0
+    # StrainCall meets the reads in the order of the position-sorted BAM
+    raw = sorted(raw, key=lambda r: r[1])
     u = StdMt19937(1234).canonical(len(raw))
     kept = [r for r, x in zip(raw, u) if not (x > rho)]
 

@@ -67,25 +67,99 @@ def test_cli_matches_reference_cli(tmp_path, spec):
     assert os.listdir(str(tmp_path)).count("genes.fa") == 1 and len(os.listdir(str(tmp_path))) == 3  # temp files removed
 
 
-@pytest.mark.gpu
-def test_cli_windows_match_reference_cli(tmp_path):
-    """Several overlapping scan windows (-w/-o): cropping of reads at window borders, window adjustment."""
+def parse_dump(path):
+    wins = []
+    for line in open(path):
+        f = line.split()
+        if f[0] == "WINDOW":
+            wins.append(dict(name=f[1], p0=int(f[2]), p1=int(f[3]), pos=[], cigar=[], seq=[], cn=[], mates=[]))
+        elif f[0] == "GENE":
+            wins[-1]["gene"] = f[1] if len(f) > 1 else ""
+        elif f[0] == "READ":
+            w = wins[-1]
+            w["pos"].append(int(f[1])); w["cigar"].append(f[2]); w["seq"].append(f[3]); w["cn"].append(int(f[4]))
+            w["mates"].append([int(x) for x in f[5:]])
+    return wins
+
+
+WINDOW_ARGS = ["-w", "120", "-o", "40", "-l", "30", "-q", "0"]
+
+
+def window_fixture(tmp_path, indels):
+    kw = dict(indel_err=0.01) if indels else dict(indel_frac=0.0)
+    gene, raw, _ = synth.simulate_raw_reads(400, 60, 2, seed=31 if indels else 33, window=(100, 400), sub_err=0.003,
+                                            divergence=(0.03, 0.06), **kw)
+    return synth.write_cli_fixture(str(tmp_path), "w1", gene, raw)
+
+
+def test_cli_io_glue_reproduces_reference_graphs(tmp_path):
+    """CPU: the scan windows, cropped reads, filters, down-sampling and de-duplication of the drop-in CLI
+    (--dump-inputs stops before the device is needed) give, window by window, the graphs the reference CLI
+    prints with -G.  The graphs are built by the product's host phases with the alignment rows supplied by
+    the test (no device here)."""
     if not os.path.exists(REF_CLI):
         pytest.skip("oracle/_ref/StrainCall not built")
-    gene, raw, _ = synth.simulate_raw_reads(400, 60, 2, seed=31, window=(100, 400), sub_err=0.003, indel_err=0.01,
-                                            divergence=(0.03, 0.06))
-    fa, sam = synth.write_cli_fixture(str(tmp_path), "w1", gene, raw)
-    args = ["-w", "120", "-o", "40", "-l", "30", "-q", "0", fa, sam]
-    code_r, out_r, err_r = run_cli(REF_CLI, args + ["-G"], str(tmp_path))
-    code, out, err = run_cli(CLI, args + ["-G"], str(tmp_path))
+    from oracle import refpy
+    fa, sam = window_fixture(tmp_path, indels=False)
+    code, out_ref, _ = run_cli(REF_CLI, WINDOW_ARGS + [fa, sam, "-G"], str(tmp_path))
+    assert code == 0
+    dump = os.path.join(str(tmp_path), "dump.txt")
+    code, _, err = run_cli(CLI, WINDOW_ARGS + [fa, sam, "--dump-inputs", dump], str(tmp_path))
     assert code == 0, err
-    assert code_r == 0
-    assert out == out_r
-    code_r, out_r, err_r = run_cli(REF_CLI, args, str(tmp_path))
-    code, out, err = run_cli(CLI, args, str(tmp_path))
+    wins = parse_dump(dump)
+    assert len(wins) >= 3
+    text = ""
+    for w in wins:
+        if not w["pos"]:
+            continue
+        b = api.StrainCallBatch()
+        b.add_subgroup(w["gene"], w["pos"], w["cigar"], w["seq"], w["cn"])
+        b.thread_reads()
+        b.finish_graphs_with_rows([refpy.msa_align(p, "oracle") for p in b.msa_problems()])
+        text += b.output_edge(0)
+    assert text == out_ref
+
+
+def test_cli_inputs_equal_synth_subgroup(tmp_path):
+    """CPU: with one window over the whole gene the CLI's reads are synth.make_subgroup's (same
+    down-sampling stream, same AlignRead order, same ReadPairs)."""
+    spec = dict(n_reads=3000, read_len=100, n_strains=3, seed=5, window=(0, 300), sub_err=0.004, paired=True,
+                divergence=(0.02, 0.05))
+    gene, raw, _ = synth.simulate_raw_reads(**spec)
+    fa, sam = synth.write_cli_fixture(str(tmp_path), "gx", gene, raw)
+    dump = os.path.join(str(tmp_path), "dump.txt")
+    code, _, err = run_cli(CLI, ["-r", "gx:1-%d" % len(gene), "-w", "5000", "-q", "0", "-l", "20", fa, sam,
+                                 "--dump-inputs", dump], str(tmp_path))
     assert code == 0, err
-    if code_r == 0:
-        assert out == out_r
+    (w,) = parse_dump(dump)
+    sg = synth.make_subgroup(**spec)
+    assert sg.n_reads < sg.n_raw_reads  # the depth cap was active
+    assert (w["gene"], w["pos"], w["cigar"], w["seq"], w["cn"]) == (sg.gene, sg.pos, sg.cigar, sg.seq, sg.cn)
+    assert [m for ms in w["mates"] for m in ms] == [int(x) for x in sg.pair_val]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("indels", [False, True])
+def test_cli_windows_match_reference_cli(tmp_path, indels):
+    """Several overlapping scan windows (-w/-o) end to end.  With indel-bearing reads the reference's own
+    cropping can leave a read that starts with an insertion at the window start; its graph construction
+    then erases set::end() (PartialOrderGraph.cpp:795-796) and may never return -- the comparison is
+    skipped when the reference does not finish, the drop-in must still finish."""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref/StrainCall not built")
+    fa, sam = window_fixture(tmp_path, indels)
+    code, out, err = run_cli(CLI, WINDOW_ARGS + [fa, sam], str(tmp_path))
+    assert code == 0, err
+    assert out.count(">contigw1") >= 3
+    try:
+        env = dict(os.environ)
+        env["PATH"] = SHIM + os.pathsep + env.get("PATH", "")
+        r = subprocess.run([REF_CLI] + WINDOW_ARGS + [fa, sam], cwd=str(tmp_path), env=env, stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, timeout=120)
+    except subprocess.TimeoutExpired:
+        pytest.skip("the reference CLI did not finish on this input")
+    if r.returncode == 0:
+        assert out == r.stdout
 
 
 @pytest.mark.gpu
