@@ -5,8 +5,16 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <random>
 #include <unordered_map>
+#include <chrono>
+#include <cstdlib>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 
 #include "dpm.cuh"
 
@@ -68,9 +76,17 @@ struct Sub
     bool branching = false, done = false, failed = false;
     std::vector<uint8_t> present;
     int levels = 0;
-    // this step
+    // this step: every subgroup stages its share privately (the host part of a level runs on all cores),
+    // the shares are then packed into one pinned arena and go to the device in one copy
     int mode = MODE_NONE, m = 0, D = 0, read_size = 0, nsweeps = 0;
     int ab_off = 0;
+    std::vector<int> I;
+    std::vector<double> Dv;
+    StepGroup sg;
+    bool has_group = false;
+    std::vector<std::pair<int, int>> ops;  // (src slot, dst slot) copies to run before the next level
+    int local_launches = 0;
+    long long step_updates = 0, step_draws = 0;
     // result
     bool have_result = false;
     std::vector<Cand> result;
@@ -120,6 +136,86 @@ void sort_desc_by_abundance(std::vector<T>& v)
     v.swap(r);
 }
 
+// Persistent workers for the per-subgroup host work of a level (a few microseconds each, thousands of levels).
+class Workers
+{
+public:
+    explicit Workers(unsigned n) : stop_(false), gen_(0), pending_(0)
+    {
+        for (unsigned t = 0; t < n; ++t) th_.emplace_back([this] { loop(); });
+    }
+    ~Workers()
+    {
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    // fn(i) for i in [0, n); returns when all are done; the first exception is rethrown
+    void run(size_t n, const std::function<void(size_t)>& fn)
+    {
+        if (n == 0) return;
+        if (th_.empty() || n == 1)
+        {
+            for (size_t i = 0; i < n; ++i) fn(i);
+            return;
+        }
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            fn_ = &fn;
+            n_ = n;
+            next_.store(0);
+            pending_ = th_.size();
+            err_ = nullptr;
+            ++gen_;
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+        if (err_) std::rethrow_exception(err_);
+    }
+
+private:
+    void loop()
+    {
+        unsigned long seen = 0;
+        for (;;)
+        {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            for (;;)
+            {
+                const size_t i = next_.fetch_add(1);
+                if (i >= n_) break;
+                try { (*fn_)(i); }
+                catch (...)
+                {
+                    std::unique_lock<std::mutex> lk(mu_);
+                    if (!err_) err_ = std::current_exception();
+                }
+            }
+            std::unique_lock<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    bool stop_;
+    unsigned long gen_;
+    size_t pending_, n_ = 0;
+    std::atomic<size_t> next_{0};
+    const std::function<void(size_t)>* fn_ = nullptr;
+    std::exception_ptr err_;
+};
+
 struct Engine
 {
     const InferParams& prm;
@@ -129,10 +225,13 @@ struct Engine
     double tau, diff, e;
     // step staging
     std::vector<StepGroup> h_groups;
-    std::vector<int> h_I;
-    std::vector<double> h_D;
+    PinBuf<StepGroup> p_groups;
+    PinBuf<int> p_I;
+    PinBuf<double> p_D, p_al;
+    size_t n_I = 0, n_D = 0;
     std::vector<InheritOp> h_ops;
     std::vector<int> group_sub;
+    std::unique_ptr<Workers> workers;
     DevBuf<StepGroup> d_groups;
     DevBuf<int> d_I;
     DevBuf<double> d_D, d_W, d_U;
@@ -158,13 +257,13 @@ struct Engine
         nll.reserve((size_t)cap * s.R);
         nsub.reserve((size_t)cap * 36);
         RAMBL_CUDA(cudaMemsetAsync(nll.p, 0, sizeof(double) * (size_t)cap * s.R, st));
-        launch_init_models(nsub.p, cap, e, st, &stats.launches);
+        launch_init_models(nsub.p, cap, e, st, &s.local_launches);
         if (s.slot_cap)
         {
             RAMBL_CUDA(cudaMemcpyAsync(nll.p, s.ll.p, sizeof(double) * (size_t)s.slot_cap * s.R, cudaMemcpyDeviceToDevice, st));
             RAMBL_CUDA(cudaMemcpyAsync(nsub.p, s.sub.p, sizeof(double) * (size_t)s.slot_cap * 36, cudaMemcpyDeviceToDevice, st));
         }
-        RAMBL_CUDA(cudaStreamSynchronize(st));
+        if (s.slot_cap) RAMBL_CUDA(cudaStreamSynchronize(st));  // the old buffers are freed below
         std::swap(s.ll.p, nll.p); std::swap(s.ll.cap, nll.cap);
         std::swap(s.sub.p, nsub.p); std::swap(s.sub.cap, nsub.cap);
         for (int k = cap - 1; k >= s.slot_cap; --k) s.free_slots.push_back(k);
@@ -184,8 +283,8 @@ struct Engine
     }
     void inherit(Sub& s, int src, int dst)
     {
-        // grow_slots may have moved the buffers: ops are resolved to pointers at launch time
-        h_ops.push_back({nullptr, (long long)(&s - &subs[0]), nullptr, src, dst});
+        // grow_slots may move the buffers: the copies are resolved to pointers when they are launched
+        s.ops.push_back({src, dst});
     }
 
     // ---- set-up --------------------------------------------------------------------------------
@@ -217,7 +316,7 @@ struct Engine
             if (!s.g->pool_chars.empty())
                 RAMBL_CUDA(cudaMemcpyAsync(s.d_pool.p, s.g->pool_chars.data(), s.g->pool_chars.size(), cudaMemcpyHostToDevice, st));
             stats.h2d_bytes += (long long)(s.g->label_chars.size() + s.g->pool_chars.size());
-            grow_slots(s, 16);
+            grow_slots(s, 64);  // growing later means a device allocation and a copy in the middle of the walk
             s.present.assign(s.R, 0);
             s.mark.assign(s.g->n_nodes, -1);
             Cand root;  // Strain(100,e), NonparametricClustering.cpp:281
@@ -260,8 +359,14 @@ struct Engine
     }
 
     // ---- one level: host part before the launches ---------------------------------------------------
-    void prepare(Sub& s, int sub_index)
+    void prepare(Sub& s)
     {
+        s.I.clear();
+        s.Dv.clear();
+        s.has_group = false;
+        s.step_updates = s.step_draws = 0;
+        std::vector<int>& h_I = s.I;
+        std::vector<double>& h_D = s.Dv;
         const FlatGraph& g = *s.g;
         std::vector<int> lv_rid, lv_so, lv_sl, lv_cn;
         s.nxt.clear();
@@ -358,16 +463,14 @@ struct Engine
         sg.nsweeps = (s.mode == MODE_GIBBS) ? std::min(prm.n, 40000 / D) : 0;
         sg.ab_off = (int)h_D.size();
         for (const Cand& c : s.cands) h_D.push_back(c.ab);
-        sg.w_off = w_total;
-        w_total += scratch_doubles(S, D);  // weights, normalisers (k_hard), letter codes (k_gibbs)
         s.D = D;
         s.read_size = D;
         s.nsweeps = sg.nsweeps;
         s.ab_off = sg.ab_off;
-        h_groups.push_back(sg);
-        group_sub.push_back(sub_index);
-        stats.loglik_updates += (long long)m * S;
-        if (s.mode == MODE_GIBBS && S >= 2) { stats.draws += (long long)D * sg.nsweeps; s.draws += (long long)D * sg.nsweeps; }
+        s.sg = sg;
+        s.has_group = true;
+        s.step_updates = (long long)m * S;
+        if (s.mode == MODE_GIBBS && S >= 2) { s.step_draws = (long long)D * sg.nsweeps; s.draws += s.step_draws; }
     }
 
     // ---- one level: host part after the launches ------------------------------------------------------
@@ -475,16 +578,51 @@ struct Engine
         }
     }
 
+    // pack the private shares of the subgroups into the pinned arenas (offsets become arena offsets)
+    void pack_step()
+    {
+        h_groups.clear();
+        group_sub.clear();
+        w_total = 0;
+        size_t ti = 0, td = 0;
+        for (const Sub& s : subs) if (s.has_group) { ti += s.I.size(); td += s.Dv.size(); }
+        p_I.reserve(std::max<size_t>(ti, 1));
+        p_D.reserve(std::max<size_t>(td, 1));
+        n_I = n_D = 0;
+        for (size_t i = 0; i < subs.size(); ++i)
+        {
+            Sub& s = subs[i];
+            if (!s.has_group) continue;
+            StepGroup sg = s.sg;
+            const int bi = (int)n_I, bd = (int)n_D;
+            if (!s.I.empty()) memcpy(p_I.p + n_I, s.I.data(), sizeof(int) * s.I.size());
+            if (!s.Dv.empty()) memcpy(p_D.p + n_D, s.Dv.data(), sizeof(double) * s.Dv.size());
+            n_I += s.I.size();
+            n_D += s.Dv.size();
+            sg.slot_off += bi; sg.lab_off += bi; sg.rid_off += bi; sg.draw_off += bi;
+            sg.ab_off += bd;
+            sg.w_off = w_total;
+            w_total += scratch_doubles(sg.S, sg.D);  // weights, normalisers (k_hard), letter codes (k_gibbs)
+            s.ab_off = sg.ab_off;
+            h_groups.push_back(sg);
+            group_sub.push_back((int)i);
+            stats.loglik_updates += s.step_updates;
+            stats.draws += s.step_draws;
+            s.has_group = false;
+        }
+    }
+
     void flush_inherits()
     {
-        if (h_ops.empty()) return;
-        for (InheritOp& op : h_ops)
+        for (size_t i = 0; i < subs.size(); ++i)
         {
-            Sub& s = subs[(size_t)op.ll_stride];
-            op.ll = s.ll.p;
-            op.sub = s.sub.p;
-            op.ll_stride = s.R;
+            Sub& s = subs[i];
+            for (const auto& c : s.ops) h_ops.push_back({s.ll.p, (long long)s.R, s.sub.p, c.first, c.second});
+            s.ops.clear();
+            stats.launches += s.local_launches;
+            s.local_launches = 0;
         }
+        if (h_ops.empty()) return;
         for (size_t b = 0; b < h_ops.size(); b += 32768)
         {
             const int n = (int)std::min<size_t>(32768, h_ops.size() - b);
@@ -497,11 +635,10 @@ struct Engine
         h_ops.clear();
     }
 
-    void run_step(std::vector<double>& al)
+    const double* run_step()
     {
         flush_inherits();
-        al.clear();
-        if (h_groups.empty()) return;
+        if (h_groups.empty()) return nullptr;
         int max_S = 0, max_m = 0, max_D = 0;
         bool any_hard = false, any_gibbs = false;
         for (size_t k = 0; k < h_groups.size(); ++k)
@@ -520,12 +657,15 @@ struct Engine
             any_gibbs = any_gibbs || sg.mode == MODE_GIBBS || sg.mode == MODE_ASSIGN;
         }
         d_groups.reserve(h_groups.size());
-        d_I.reserve(std::max<size_t>(1, h_I.size()));
-        d_D.reserve(std::max<size_t>(1, h_D.size()));
+        d_I.reserve(std::max<size_t>(1, n_I));
+        d_D.reserve(std::max<size_t>(1, n_D));
         d_W.reserve(std::max<long long>(1, w_total));
-        RAMBL_CUDA(cudaMemcpyAsync(d_groups.p, h_groups.data(), sizeof(StepGroup) * h_groups.size(), cudaMemcpyHostToDevice, st));
-        RAMBL_CUDA(cudaMemcpyAsync(d_I.p, h_I.data(), sizeof(int) * h_I.size(), cudaMemcpyHostToDevice, st));
-        RAMBL_CUDA(cudaMemcpyAsync(d_D.p, h_D.data(), sizeof(double) * h_D.size(), cudaMemcpyHostToDevice, st));
+        p_groups.reserve(h_groups.size());
+        p_al.reserve(std::max<size_t>(1, n_D));
+        memcpy(p_groups.p, h_groups.data(), sizeof(StepGroup) * h_groups.size());
+        RAMBL_CUDA(cudaMemcpyAsync(d_groups.p, p_groups.p, sizeof(StepGroup) * h_groups.size(), cudaMemcpyHostToDevice, st));
+        if (n_I) RAMBL_CUDA(cudaMemcpyAsync(d_I.p, p_I.p, sizeof(int) * n_I, cudaMemcpyHostToDevice, st));
+        if (n_D) RAMBL_CUDA(cudaMemcpyAsync(d_D.p, p_D.p, sizeof(double) * n_D, cudaMemcpyHostToDevice, st));
         StepLaunch L;
         L.groups = d_groups.p; L.n_groups = (int)h_groups.size(); L.iarena = d_I.p; L.darena = d_D.p;
         L.weights = d_W.p; L.uniforms = d_U.p; L.n_uniforms = kUniforms; L.counters = d_counters.p;
@@ -544,13 +684,13 @@ struct Engine
                 if ((sg.mode == MODE_GIBBS || sg.mode == MODE_ASSIGN) && sg.S >= 2)
                     stats.gibbs_bytes += (long long)sg.nsweeps * sg.D * (sg.S + 1) * 8;
         }
-        stats.h2d_bytes += (long long)(sizeof(StepGroup) * h_groups.size() + sizeof(int) * h_I.size() + sizeof(double) * h_D.size());
-        stats.d2h_bytes += (long long)(sizeof(double) * h_D.size());
+        stats.h2d_bytes += (long long)(sizeof(StepGroup) * h_groups.size() + sizeof(int) * n_I + sizeof(double) * n_D);
+        stats.d2h_bytes += (long long)(sizeof(double) * n_D);
         launch_level_step(L, st, &stats.launches);
-        al.resize(h_D.size());
-        RAMBL_CUDA(cudaMemcpyAsync(al.data(), d_D.p, sizeof(double) * h_D.size(), cudaMemcpyDeviceToHost, st));
+        RAMBL_CUDA(cudaMemcpyAsync(p_al.p, d_D.p, sizeof(double) * n_D, cudaMemcpyDeviceToHost, st));
         RAMBL_CUDA(cudaStreamSynchronize(st));
         stats.level_steps += 1;
+        return p_al.p;
     }
 
     void collect_kernel_times()
@@ -571,20 +711,20 @@ struct Engine
         }
     }
 
-    void reset_step()
-    {
-        h_groups.clear(); h_I.clear(); h_D.clear(); group_sub.clear();
-        w_total = 0;
-    }
 
     // ---- read_assign for every subgroup in one step, NonparametricClustering.cpp:776-836 ----
-    void assign_step(std::vector<double>& al)
+    const double* assign_step()
     {
-        reset_step();
         for (size_t i = 0; i < subs.size(); ++i)
         {
             Sub& s = subs[i];
             s.mode = MODE_NONE;
+            s.has_group = false;
+            s.I.clear();
+            s.Dv.clear();
+            s.step_updates = s.step_draws = 0;
+            std::vector<int>& h_I = s.I;
+            std::vector<double>& h_D = s.Dv;
             if (s.status != RAMBL_OK || s.result.empty()) continue;
             const SubgroupInput& in = *s.in;
             const int S = (int)s.result.size(), R = s.g->n_reads;
@@ -616,15 +756,13 @@ struct Engine
                 }
             sg.ab_off = (int)h_D.size();
             for (const Cand& c : s.result) h_D.push_back(c.ab);
-            sg.w_off = w_total;
-            w_total += scratch_doubles(S, D);
             s.mode = MODE_ASSIGN;
-            s.ab_off = sg.ab_off;
-            h_groups.push_back(sg);
-            group_sub.push_back((int)i);
-            if (S >= 2) { stats.draws += (long long)D * sg.nsweeps; s.draws += (long long)D * sg.nsweeps; }
+            s.sg = sg;
+            s.has_group = true;
+            if (S >= 2) { s.step_draws = (long long)D * sg.nsweeps; s.draws += s.step_draws; }
         }
-        run_step(al);
+        pack_step();
+        return run_step();
     }
 };
 
@@ -660,27 +798,41 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
     RAMBL_CUDA(cudaEventCreate(&e1));
     RAMBL_CUDA(cudaEventRecord(e0, stream));
     E.start(in);
-    std::vector<double> al;
+    {
+        unsigned nt = std::thread::hardware_concurrency();
+        nt = std::min<unsigned>(nt ? nt : 1, 32);
+        if (E.subs.size() >= 4 && nt > 1) E.workers.reset(new Workers(std::min<size_t>(nt, E.subs.size())));
+    }
+    double trace[4] = {0, 0, 0, 0};
+    auto for_subs = [&](const std::function<void(size_t)>& fn) {
+        if (E.workers) E.workers->run(E.subs.size(), fn);
+        else for (size_t i = 0; i < E.subs.size(); ++i) fn(i);
+    };
     for (;;)
     {
-        E.reset_step();
         bool any = false;
-        for (size_t i = 0; i < E.subs.size(); ++i)
-        {
-            Sub& s = E.subs[i];
-            if (s.done) continue;
-            any = true;
-            E.prepare(s, (int)i);
-        }
+        for (const Sub& s : E.subs) any = any || !s.done;
         if (!any) break;
-        E.run_step(al);
-        for (size_t i = 0; i < E.subs.size(); ++i)
-        {
+        const auto t0 = std::chrono::steady_clock::now();
+        for_subs([&](size_t i) { if (!E.subs[i].done) E.prepare(E.subs[i]); });
+        const auto t1 = std::chrono::steady_clock::now();
+        E.pack_step();
+        const auto t2 = std::chrono::steady_clock::now();
+        const double* al = E.run_step();
+        const auto t3 = std::chrono::steady_clock::now();
+        for_subs([&](size_t i) {
             Sub& s = E.subs[i];
-            if (s.done) continue;
-            E.advance(s, s.mode == MODE_NONE ? nullptr : al.data() + s.ab_off);
-        }
+            if (s.done) return;
+            E.advance(s, s.mode == MODE_NONE ? nullptr : al + s.ab_off);
+        });
+        const auto t4 = std::chrono::steady_clock::now();
+        trace[0] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        trace[1] += std::chrono::duration<double, std::milli>(t2 - t1).count();
+        trace[2] += std::chrono::duration<double, std::milli>(t3 - t2).count();
+        trace[3] += std::chrono::duration<double, std::milli>(t4 - t3).count();
     }
+    if (getenv("RAMBL_TRACE"))
+        fprintf(stderr, "[rambl] host ms: prepare %.1f pack %.1f device-step %.1f advance %.1f\n", trace[0], trace[1], trace[2], trace[3]);
     for (Sub& s : E.subs)
         if (!s.have_result && !s.failed) s.status = RAMBL_ERR_NO_STRAINS;
     std::vector<std::vector<double>> infer_ab(E.subs.size());
@@ -688,7 +840,7 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
         for (const Cand& c : E.subs[i].result) infer_ab[i].push_back(c.ab);
     if (prm.assign)
     {
-        E.assign_step(al);
+        const double* al = E.assign_step();
         for (Sub& s : E.subs)
             if (s.mode == MODE_ASSIGN)
                 for (size_t k = 0; k < s.result.size(); ++k) s.result[k].ab = al[s.ab_off + k];
