@@ -14,7 +14,7 @@
 
 namespace rambl {
 
-constexpr int DPM_SMAX = 128;  // candidate strains per subgroup and level (the reference prunes to ~80)
+constexpr int DPM_SMAX = 256;  // candidate strains per subgroup and level (the reference prunes to ~80)
 
 enum { MODE_NONE = 0, MODE_HARD = 1, MODE_GIBBS = 2, MODE_ASSIGN = 3 };
 

@@ -144,6 +144,23 @@ def test_paired_reads_and_copies():
     assert compare_strains(want, got) == []
 
 
+@pytest.mark.parametrize("n,ie,W", [(200, 0.002, 450), (400, 0.001, 600)])
+def test_config4_like_indel_rich_250bp_reads(n, ie, W):
+    """BASELINE configs[4] at a size the oracle finishes: 250bp reads, homopolymer-biased indel errors and
+    indel-bearing strains (wide graphs, insertion alignment on the device), against the oracle."""
+    sg = synth.make_subgroup(n, 250, 3, indel_err=ie, indel_frac=0.3, homopolymer_bias=True, seed=4,
+                             window=(300, 300 + W), divergence=(0.01, 0.03))
+    o = refpy.RefPog(sg.gene, sg.pos, sg.cigar, sg.seq, sg.cn, variant="oracle")
+    want, _ = o.infer(sg.pair_off, sg.pair_val)
+    assert len(want["final"]) > 0
+    b = _solve([sg])
+    assert b.status(0) == api.RAMBL_OK
+    assert strip_sib(b.graph_dump(0)) == strip_sib(o.dump())
+    assert b.output_edge(0) == o.edges()
+    got = refpy.parse_strain_dump(b.strains_text(0))
+    assert compare_strains(want, got) == []
+
+
 def test_config0_scale_properties():
     """BASELINE configs[0]-like input (2k 100bp reads, 3 strains, whole 16S gene): too slow for the oracle,
     so check what must hold at any size: deterministic, abundances normalised, every strain a ^...$ path
