@@ -153,6 +153,11 @@ def cpu_baseline_block(window: int, cores: int = 1):
                       "16S gene, graph build + infer_strains + read_assign, %.1f s; %s" % (sg.n_reads, window, dt, FULL_SIZE_NOTE)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_gibbs launch of this workload, from the ncu --set full
+# capture summarised in profiles/r01_k_gibbs_full.txt (825 KB read, 0 written: the weight tiles once; the
+# sweeps re-read them from L2 / shared memory)
+GIBBS_DRAM_BYTES_PER_LAUNCH = 824832
+
 FULL_SIZE_NOTE = ("the reference on the FULL configs[1] subgroup (8223 reads after down-sampling), measured once on one "
                   "core of the build container with oracle/_ref -O2: 805 s = 10.2 reads/s; windowed samples run faster "
                   "per read because fewer candidate strains accumulate")
@@ -194,6 +199,36 @@ def run_reference_arm(args, rank, world):
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
+
+
+def poa_block():
+    """The other half of BASELINE.json's metric ("POA GCUPS"): the insertion-alignment kernel on a fixed batch of
+    2000 level-problems as deep homopolymer levels produce them (20-400 insertion strings of 1-9 letters each).
+    Outside the timed region; cells = profile columns x letters per alignment step, CUDA-event kernel time."""
+    import numpy as np
+    from rambl_b200 import api
+    rnd = np.random.default_rng(1)
+    probs = []
+    for _ in range(2000):
+        n = int(rnd.integers(20, 400))
+        hp = "ACGT"[int(rnd.integers(4))]
+        seqs = []
+        for _ in range(n):
+            k = int(rnd.integers(1, 10))
+            s = [hp] * k
+            if rnd.random() < 0.1:
+                s[int(rnd.integers(k))] = "ACGT"[int(rnd.integers(4))]
+            seqs.append("".join(s))
+        probs.append(sorted(seqs, key=lambda x: -len(x)))
+    api.msa_align_batch(probs)
+    best = None
+    for _ in range(3):
+        _, st = api.msa_align_batch(probs)
+        if best is None or st["kernel_ms"] < best["kernel_ms"]:
+            best = st
+    return {"gcups": best["dp_cells"] / best["kernel_ms"] / 1e6, "dp_cells": best["dp_cells"], "kernel_ms": best["kernel_ms"],
+            "alignment_steps_per_s": sum(len(p) - 1 for p in probs) / (best["kernel_ms"] / 1e3),
+            "workload": "2000 insertion-alignment problems, 423k homopolymer insertion strings of 1-9 letters"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -297,12 +332,16 @@ def main():
     gibbs_s = agg.get("gibbs_kernel_ms", 0.0) / 1000.0
     achieved = (agg.get("gibbs_alg_bytes", 0) / 1e9) / gibbs_s if gibbs_s > 0 else 0.0
     roofline = {"kernel": "k_gibbs (speculative block Gibbs sweeps)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": GIBBS_DRAM_BYTES_PER_LAUNCH,
+                "algorithmic_bytes_per_launch": (agg.get("gibbs_alg_bytes", 0) / agg["gibbs_launches"]) if agg.get("gibbs_launches") else None,
+                "avg_launch_ms": (agg.get("gibbs_kernel_ms", 0.0) / agg["gibbs_launches"]) if agg.get("gibbs_launches") else None,
+                "peak_source": peak_src,
                 "share_of_infer_time": (agg.get("gibbs_kernel_ms", 0.0) / infer_ms) if infer_ms else None,
                 "draws_per_s": agg.get("draws", 0) / gibbs_s if gibbs_s > 0 else None,
                 "passes_per_round": (agg.get("gibbs_passes", 0) / agg["gibbs_rounds"]) if agg.get("gibbs_rounds") else None,
                 "note": "a sequential Gibbs chain per subgroup: latency-bound by construction, its weights stay in L2/shared "
                         "memory; the algorithmic bytes are sweeps x draws x (S weights + 1 uniform) x 8"}
+    poa = poa_block()
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cpu = cpu_baseline_block(args.cpu_sample_window)
@@ -318,9 +357,8 @@ def main():
                    "result_bytes_per_step": int(out_bytes / K)},
            "gpu_launches": int(launches),
            "roofline": roofline,
-           "poa": {"msa_problems_per_step": agg.get("msa_problems", 0) / K, "msa_dp_cells_per_step": agg.get("msa_dp_cells", 0) / K,
-                   "msa_kernel_ms_per_step": agg.get("msa_kernel_ms", 0.0) / K,
-                   "gcups": (agg.get("msa_dp_cells", 0) / 1e9) / (agg["msa_kernel_ms"] / 1e3) if agg.get("msa_kernel_ms") else None},
+           "poa": dict(poa, msa_problems_in_step=agg.get("msa_problems", 0) / K,
+                       msa_dp_cells_in_step=agg.get("msa_dp_cells", 0) / K),
            "level_steps_per_step": agg.get("level_steps", 0) / K, "draws_per_step": agg.get("draws", 0) / K}
     if cpu is not None:
         out["cpu_baseline"] = cpu
