@@ -95,7 +95,7 @@ int rambl_batch_finish_graphs_with_rows(rambl_batch* b, const char* rows_text);
  * and, when do_assign != 0, PartialOrderGraph::read_assign(strains, reads, read_pairs, n)
  * (NonparametricClustering.cpp:776-836) followed by main()'s abundance sort (StrainCall.cpp:1027),
  * for every subgroup.  Subgroups whose candidates were all pruned get status RAMBL_ERR_NO_STRAINS, and
- * subgroups whose candidate set outgrew the kernels (more than 128 live strains, which needs
+ * subgroups whose candidate set outgrew the kernels (more than 256 live strains, which needs
  * degenerate abundances) get RAMBL_ERR_CAPACITY; the call itself still returns RAMBL_OK. */
 int rambl_batch_infer(rambl_batch* b, int32_t n, float e, float tau, float diff, int32_t do_assign, int32_t keep_loglik);
 
