@@ -79,6 +79,20 @@ int rambl_batch_add_subgroup(rambl_batch* b, const char* gene, int32_t n_reads, 
                              const char* const* cigar, const char* const* seq, const int32_t* copies,
                              const int32_t* pair_off, const int32_t* pair_val);
 
+/* A subgroup whose graph was built elsewhere (e.g. by the reference's own PartialOrderGraph): the `nodes`
+ * vector flattened in order.  Node u has AlignState state[u] (mat=0, mis, ins, del; PartialOrderGraph.hpp:82),
+ * label label_chars[label_off[u]..label_off[u+1]), ordered successors out_to[out_off[u]..out_off[u+1]) and an
+ * ordered read pool: entry e has read id pool_rid[e], copy number pool_copies[e] and letters
+ * pool_chars[pool_str_off[e]..pool_str_off[e+1]).  Node 0 must be "^", exactly one node "$".  read_copies[r] is
+ * the copy number of unique read r; pairs as in rambl_batch_add_subgroup.  The reads-over-edge counts
+ * (number_of_reads_cover_nodes, PartialOrderGraph.cpp:1218-1244) are derived here.  Such a subgroup is ready
+ * for rambl_batch_infer at once.  Returns the subgroup index (>= 0) or -error. */
+int rambl_batch_add_graph(rambl_batch* b, int32_t n_nodes, int32_t n_reads, const uint8_t* state,
+                          const int32_t* label_off, const char* label_chars, const int32_t* out_off,
+                          const int32_t* out_to, const int32_t* pool_off, const int32_t* pool_rid,
+                          const int32_t* pool_copies, const int32_t* pool_str_off, const char* pool_chars,
+                          const int32_t* read_copies, const int32_t* pair_off, const int32_t* pair_val);
+
 /* PartialOrderGraph::build (PartialOrderGraph.cpp:67-265) for every subgroup added so far; the
  * insertion alignments of all subgroups run in one device launch. */
 int rambl_batch_build_graphs(rambl_batch* b);

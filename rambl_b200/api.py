@@ -59,6 +59,8 @@ SYMBOLS = {
     "rambl_batch_create": (C.c_void_p, []),
     "rambl_batch_destroy": (None, [C.c_void_p]),
     "rambl_batch_add_subgroup": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, _i32p, _strp, _strp, _i32p, _i32p, _i32p]),
+    "rambl_batch_add_graph": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint8), _i32p, C.c_char_p, _i32p, _i32p,
+                                        _i32p, _i32p, _i32p, _i32p, C.c_char_p, _i32p, _i32p, _i32p]),
     "rambl_batch_build_graphs": (C.c_int, [C.c_void_p]),
     "rambl_batch_thread_reads": (C.c_int, [C.c_void_p]),
     "rambl_batch_msa_problems_text": (C.c_void_p, [C.c_void_p]),
@@ -221,6 +223,33 @@ class StrainCallBatch:
         self._nreads.append(n)
         return rc
 
+    def add_graph(self, nodes: Sequence[dict], read_copies, pair_off=None, pair_val=None) -> int:
+        """Add a subgroup whose graph was built elsewhere.  ``nodes`` is the `nodes` vector in order, each a dict
+        with st (AlignState 0..3), label, out (ordered successor ids) and pool (ordered (rid, letters, copies))."""
+        n = len(nodes)
+        st = np.asarray([nd["st"] for nd in nodes], dtype=np.uint8)
+        lab_off, out_off, pool_off, str_off = [0], [0], [0], [0]
+        labs, outs, rid, cn, strs = [], [], [], [], []
+        for nd in nodes:
+            labs.append(nd["label"]); lab_off.append(lab_off[-1] + len(nd["label"]))
+            outs.extend(nd["out"]); out_off.append(len(outs))
+            for (r, s, c) in nd["pool"]:
+                rid.append(r); cn.append(c); strs.append(s); str_off.append(str_off[-1] + len(s))
+            pool_off.append(len(rid))
+        rc_ = _i32(read_copies)
+        arrs = [_i32(x) for x in (lab_off, out_off, outs or [0], pool_off, rid or [0], cn or [0], str_off)]
+        po = _i32(pair_off) if pair_off is not None else None
+        pv = _i32(pair_val) if pair_val is not None else None
+        p = lambda a_: a_.ctypes.data_as(_i32p)
+        rc = lib().rambl_batch_add_graph(
+            self._h, n, len(rc_), st.ctypes.data_as(C.POINTER(C.c_uint8)), p(arrs[0]), "".join(labs).encode(), p(arrs[1]),
+            p(arrs[2]), p(arrs[3]), p(arrs[4]), p(arrs[5]), p(arrs[6]), "".join(strs).encode(), p(rc_),
+            p(po) if po is not None else None, p(pv) if pv is not None else None)
+        if rc < 0:
+            _check(-rc)
+        self._nreads.append(len(rc_))
+        return rc
+
     def add(self, sg) -> int:
         """Add a rambl_b200.synth.Subgroup."""
         return self.add_subgroup(sg.gene, sg.pos, sg.cigar, sg.seq, sg.cn, sg.pair_off, sg.pair_val)
@@ -312,18 +341,43 @@ class StrainCallBatch:
 
 # ------------------------------------------------------------------------------------------------
 class PartialOrderGraph:
-    """PartialOrderGraph(G, R) for one subgroup (PartialOrderGraph.hpp:231-357)."""
+    """PartialOrderGraph(G, R) for one subgroup (PartialOrderGraph.hpp:231-357).
 
-    def __init__(self, G: str, R: Sequence[tuple]):
-        self._b = StrainCallBatch()
-        pos = [r[0] for r in R]
-        cigar = [r[1] for r in R]
-        seq = [r[2] for r in R]
-        cn = [r[4] if len(r) > 4 else 1 for r in R]
-        self._cn = cn
-        self._b.add_subgroup(G, pos, cigar, seq, cn)
-        self._b.build_graphs()
+    ``R`` holds AlignRead tuples (pos, cigar, seq, qual, copies).  ``read_pairs`` is the reference's
+    ReadPairs (dict uid -> list with one mate uid or -1 per copy); it can be given here or to
+    infer_strains / read_assign like in the reference -- the graph does not depend on it."""
+
+    def __init__(self, G: str, R: Sequence[tuple], read_pairs=None):
+        self._G = G
+        self._pos = [r[0] for r in R]
+        self._cigar = [r[1] for r in R]
+        self._seq = [r[2] for r in R]
+        self._cn = [r[4] if len(r) > 4 else 1 for r in R]
         self._pairs = None
+        self._b = None
+        self._make(read_pairs)
+
+    def _csr(self, read_pairs):
+        off, val = [0], []
+        for u in range(len(self._cn)):
+            mates = read_pairs.get(u) if isinstance(read_pairs, dict) else read_pairs[u]
+            mates = list(mates) if mates is not None else [-1] * self._cn[u]
+            if len(mates) < self._cn[u]:
+                raise RamblError(RAMBL_ERR_INVALID, "ReadPairs needs one entry per read copy (uid %d)" % u)
+            val.extend(int(m) for m in mates)
+            off.append(len(val))
+        return off, val
+
+    def _make(self, read_pairs):
+        if self._b is not None and (read_pairs is None or read_pairs == self._pairs):
+            return
+        off = val = None
+        if read_pairs is not None:
+            off, val = self._csr(read_pairs)
+        b = StrainCallBatch()
+        b.add_subgroup(self._G, self._pos, self._cigar, self._seq, self._cn, off, val)
+        b.build_graphs()
+        self._b, self._pairs = b, read_pairs
 
     @property
     def N(self) -> int:
@@ -332,31 +386,21 @@ class PartialOrderGraph:
     def output_edge(self) -> str:
         return self._b.output_edge(0)
 
-    def _set_pairs(self, read_pairs):
-        if read_pairs is None:
-            return
-        off = [0]
-        val: List[int] = []
-        for u in range(len(self._cn)):
-            mates = list(read_pairs.get(u, [-1] * self._cn[u])) if isinstance(read_pairs, dict) else list(read_pairs[u])
-            val.extend(mates)
-            off.append(len(val))
-        # the subgroup was added without pairs; rebuild it with them (graphs do not depend on pairs)
-        raise RamblError(RAMBL_ERR_STATE, "pass read_pairs to StrainCallBatch.add_subgroup for paired data")
-
     def infer_strains(self, read_pairs=None, n: int = 5000, e: float = 0.01, tau: float = 0.02, diff: float = 0.01):
-        if read_pairs is not None:
-            self._set_pairs(read_pairs)
+        """streaming_clustering: the strains in the order the reference leaves them in `strains`."""
+        self._make(read_pairs)
         self._b.infer(n, e, tau, diff, assign=False)
         if self._b.status(0) != RAMBL_OK:
-            raise RamblError(self._b.status(0), "every candidate strain was pruned")
+            raise RamblError(self._b.status(0), "no strain survived (the reference is undefined on this input)")
         return self._b.strains(0)
 
     def read_assign(self, strains=None, reads=None, read_pairs=None, n: int = 5000, e: float = 0.01,
                     tau: float = 0.02, diff: float = 0.01):
-        """infer_strains + read_assign + the abundance sort of StrainCall's main(); returns the sorted strains."""
+        """infer_strains + read_assign + the abundance sort of StrainCall's main(); returns the sorted strains
+        (the device keeps the per-read likelihoods of the strains, so the two steps run as one call)."""
+        self._make(read_pairs)
         self._b.infer(n, e, tau, diff, assign=True)
         if self._b.status(0) != RAMBL_OK:
-            raise RamblError(self._b.status(0), "every candidate strain was pruned")
+            raise RamblError(self._b.status(0), "no strain survived (the reference is undefined on this input)")
         st = self._b.strains(0)
         return [st[k] for k in self._b.order(0)]

@@ -287,6 +287,71 @@ int rambl_batch_add_subgroup(rambl_batch* b, const char* gene, int32_t n_reads, 
     return rc == RAMBL_OK ? index : -rc;
 }
 
+int rambl_batch_add_graph(rambl_batch* b, int32_t n_nodes, int32_t n_reads, const uint8_t* state,
+                          const int32_t* label_off, const char* label_chars, const int32_t* out_off,
+                          const int32_t* out_to, const int32_t* pool_off, const int32_t* pool_rid,
+                          const int32_t* pool_copies, const int32_t* pool_str_off, const char* pool_chars,
+                          const int32_t* read_copies, const int32_t* pair_off, const int32_t* pair_val)
+{
+    int index = -1;
+    int rc = guarded([&] {
+        if (!b || n_nodes < 2 || n_reads < 0 || !state || !label_off || !label_chars || !out_off || !pool_off ||
+            (n_reads > 0 && !read_copies))
+            throw Error(RAMBL_ERR_INVALID, "null or empty graph argument");
+        std::unique_ptr<Subgroup> s(new Subgroup);
+        FlatGraph& g = s->graph;
+        g.n_nodes = n_nodes;
+        g.n_reads = n_reads;
+        g.st.assign(state, state + n_nodes);
+        g.level.assign(n_nodes, -1);
+        g.label_off.assign(label_off, label_off + n_nodes + 1);
+        g.label_chars.assign(label_chars, label_chars + label_off[n_nodes]);
+        g.out_off.assign(out_off, out_off + n_nodes + 1);
+        if (out_off[n_nodes]) g.out_to.assign(out_to, out_to + out_off[n_nodes]);
+        g.in_off.assign(n_nodes + 1, 0);
+        g.pool_off.assign(pool_off, pool_off + n_nodes + 1);
+        const int ne = pool_off[n_nodes];
+        if (ne)
+        {
+            if (!pool_rid || !pool_copies || !pool_str_off || !pool_chars) throw Error(RAMBL_ERR_INVALID, "null pool argument");
+            g.pool_rid.assign(pool_rid, pool_rid + ne);
+            g.pool_cn.assign(pool_copies, pool_copies + ne);
+            g.pool_str_off.assign(pool_str_off, pool_str_off + ne + 1);
+            g.pool_chars.assign(pool_chars, pool_chars + pool_str_off[ne]);
+        }
+        else g.pool_str_off.assign(1, 0);
+        for (int v : g.out_to) if (v < 0 || v >= n_nodes) throw Error(RAMBL_ERR_INVALID, "edge target out of range");
+        for (int r : g.pool_rid) if (r < 0 || r >= n_reads) throw Error(RAMBL_ERR_INVALID, "read id out of range");
+        for (int u = 0; u < n_nodes; ++u)
+            if (g.label_off[u + 1] - g.label_off[u] == 1 && g.label_chars[g.label_off[u]] == '$') g.end_node = u;
+        if (g.label(0) != "^" || g.end_node < 0) throw Error(RAMBL_ERR_INVALID, "node 0 must be '^' and one node must be '$'");
+        fill_edge_cover(g);
+        s->input.read_cn.assign(read_copies, read_copies + n_reads);
+        if (pair_off && pair_val)
+        {
+            s->input.pair_off.assign(pair_off, pair_off + n_reads + 1);
+            s->input.pair_val.assign(pair_val, pair_val + pair_off[n_reads]);
+        }
+        else
+        {
+            s->input.pair_off.assign(1, 0);
+            for (int i = 0; i < n_reads; ++i)
+            {
+                s->input.pair_val.insert(s->input.pair_val.end(), read_copies[i], -1);
+                s->input.pair_off.push_back((int)s->input.pair_val.size());
+            }
+        }
+        s->input.graph = &s->graph;
+        s->built = true;
+        // keep the bookkeeping of the read-threading phases in step: this subgroup needs neither
+        if (b->threaded_upto == b->subs.size()) b->threaded_upto += 1;
+        else throw Error(RAMBL_ERR_STATE, "add graphs before adding read subgroups, or build the pending subgroups first");
+        b->subs.push_back(std::move(s));
+        index = (int)b->subs.size() - 1;
+    });
+    return rc == RAMBL_OK ? index : -rc;
+}
+
 int rambl_batch_thread_reads(rambl_batch* b)
 {
     return guarded([&] {

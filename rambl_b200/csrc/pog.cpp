@@ -676,6 +676,33 @@ void GraphBuilder::finish(const MsaResult& rows, FlatGraph& out)
     m->flatten(out);
 }
 
+void fill_edge_cover(FlatGraph& g)
+{
+    g.out_cover.assign(g.out_to.size(), 0);
+    std::vector<int> a;
+    for (int u = 0; u < g.n_nodes; ++u)
+    {
+        a.assign(g.pool_rid.begin() + g.pool_off[u], g.pool_rid.begin() + g.pool_off[u + 1]);
+        std::sort(a.begin(), a.end());
+        int own = 0;
+        for (int e = g.pool_off[u]; e < g.pool_off[u + 1]; ++e) own += g.pool_cn[e];
+        for (int e = g.out_off[u]; e < g.out_off[u + 1]; ++e)
+        {
+            const int v = g.out_to[e];
+            int n = 0;
+            if (u == 0) { for (int q = g.pool_off[v]; q < g.pool_off[v + 1]; ++q) n += g.pool_cn[q]; }
+            else if (v == g.end_node) n = own;
+            else
+                for (int q = g.pool_off[v]; q < g.pool_off[v + 1]; ++q)
+                {
+                    auto range = std::equal_range(a.begin(), a.end(), g.pool_rid[q]);
+                    n += (int)(range.second - range.first) * g.pool_cn[q];
+                }
+            g.out_cover[e] = n;
+        }
+    }
+}
+
 std::string FlatGraph::dump() const
 {
     std::ostringstream os;

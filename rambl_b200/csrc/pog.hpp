@@ -56,6 +56,10 @@ struct FlatGraph
     std::string edges() const;  // PartialOrderGraph::output_edge
 };
 
+// number_of_reads_cover_nodes (PartialOrderGraph.cpp:1218-1244) for every edge of a flat graph whose
+// out_cover is still empty (graphs handed in from outside)
+void fill_edge_cover(FlatGraph& g);
+
 class GraphBuilder
 {
 public:

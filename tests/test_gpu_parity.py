@@ -123,6 +123,68 @@ def test_strains_match_oracle(seed):
     assert [s["path"] for s in want["final"]] == [s["path"] for s in got["final"]]
 
 
+@pytest.mark.parametrize("seed", [1, 6, 15])
+def test_strain_search_on_a_graph_built_elsewhere(seed):
+    """the host keeps its own graph builder (here: the oracle's node list, or the
+    real reference's when oracle/_ref is present) and only the strain search runs on the device."""
+    sg = synth.make_subgroup(**fuzz_spec(seed))
+    variant = "" if refpy.available("") else "oracle"
+    o = refpy.RefPog(sg.gene, sg.pos, sg.cigar, sg.seq, sg.cn, variant=variant)
+    want, _ = o.infer(sg.pair_off, sg.pair_val)
+    b = api.StrainCallBatch()
+    b.add_graph(refpy.parse_graph_dump(o.dump()), sg.cn, sg.pair_off, sg.pair_val)
+    b.infer(keep_loglik=True)
+    assert b.status(0) == api.RAMBL_OK
+    got = refpy.parse_strain_dump(b.strains_text(0))
+    assert compare_strains(want, got) == []
+
+
+def test_unusual_letters_and_clips():
+    """N in the gene (the strain letter then copies the read letter, NonparametricClustering.cpp:358),
+    soft clips and '='/'X' CIGAR
+    operations (parse_cigar), duplicate reads (copy numbers > 1).  (Reads with N never reach the graph:
+    StrainCall.cpp:547-550 drops them.)"""
+    gene = "ACGTNACGTTGCATGCAAGGNTTACGATCGATTACGGATCCAT"
+    reads = [(0, "43M", gene.replace("N", "A"), 3), (0, "43M", gene.replace("N", "C"), 2),
+             (2, "10=1X9M", "GTAACGTTGCTTGCAAGGCT", 1), (5, "2S12M", "TTACGTTGCATGCA", 1),
+             (8, "6M1I8M", "TTGCATAGCAAGGAT", 2), (8, "6M2D8M", "TTGCATCAAGGCTT", 1),
+             (20, "23M", "CTTACGATCGATTACGGATCCAT", 1), (1, "12M", "CGTCACGTTGCA", 1)]
+    pos, cig, seq, cn = zip(*reads)
+    o = refpy.RefPog(gene, pos, cig, seq, cn, variant="oracle")
+    pair_off = [0]
+    for c in cn:
+        pair_off.append(pair_off[-1] + c)
+    pair_val = [-1] * pair_off[-1]
+    want, _ = o.infer(pair_off, pair_val)
+    b = api.StrainCallBatch()
+    b.add_subgroup(gene, pos, cig, seq, cn)
+    b.build_graphs()
+    assert strip_sib(b.graph_dump(0)) == strip_sib(o.dump())
+    b.infer(keep_loglik=True)
+    if len(want["infer"]) == 0:
+        assert b.status(0) != api.RAMBL_OK
+        return
+    assert b.status(0) == api.RAMBL_OK
+    got = refpy.parse_strain_dump(b.strains_text(0))
+    assert compare_strains(want, got) == []
+
+
+def test_batch_with_an_empty_and_a_readless_subgroup():
+    """A batch where one subgroup has no reads at all (StrainCall skips such windows, StrainCall.cpp:1009)
+    next to normal ones: the others are unaffected."""
+    sg = synth.make_subgroup(**fuzz_spec(2))
+    b = api.StrainCallBatch()
+    b.add(sg)
+    b.add_subgroup("ACGTACGTAC", [], [], [], [])
+    b.add(sg)
+    b.build_graphs()
+    b.infer()
+    assert b.status(0) == api.RAMBL_OK and b.status(2) == api.RAMBL_OK
+    assert b.strains_text(0) == b.strains_text(2)
+    # the backbone-only graph has one path and no reads: one strain, abundance 1 after read_assign's normalise
+    assert b.status(1) in (api.RAMBL_OK, api.RAMBL_ERR_NO_STRAINS)
+
+
 def test_batch_equals_one_by_one():
     """Subgroups solved together (one launch set per level) give what they give alone."""
     sgs = [synth.make_subgroup(**fuzz_spec(s)) for s in (1, 2, 6, 9, 15)]

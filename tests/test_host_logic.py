@@ -136,3 +136,20 @@ def test_synthetic_downsampling_follows_std_mt19937():
     raw = synth.StdMt19937(1234).raw(2)
     assert int(raw[0]) == 822569775 and int(raw[1]) == 2137449171
     assert abs(u[0] - (822569775 + 2137449171 * 4294967296.0) / 18446744073709551616.0) < 1e-18
+
+
+def test_graph_built_elsewhere_gets_the_reference_edge_counts():
+    """rambl_batch_add_graph: a graph flattened from the oracle's node list; the reads-over-edge counts the
+    library derives must be the ones output_edge prints."""
+    for seed in (3, 9, 12):
+        sg = synth.make_subgroup(**fuzz_spec(seed))
+        o = refpy.RefPog(sg.gene, sg.pos, sg.cigar, sg.seq, sg.cn, variant="oracle")
+        b = api.StrainCallBatch()
+        b.add_graph(refpy.parse_graph_dump(o.dump()), sg.cn, sg.pair_off, sg.pair_val)
+        assert b.num_nodes(0) == o.num_nodes()
+        mine = [l for l in b.output_edge(0).split("\n") if l and not l.startswith("#")]
+        want = [l for l in o.edges().split("\n") if l and not l.startswith("#")]
+        assert mine == want
+    bad = api.StrainCallBatch()
+    with pytest.raises(api.RamblError):
+        bad.add_graph([dict(st=0, label="A", out=[1], pool=[]), dict(st=0, label="$", out=[], pool=[])], [])
