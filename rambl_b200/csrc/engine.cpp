@@ -22,6 +22,8 @@ namespace rambl {
 
 namespace {
 
+// 80 candidates plus their children before the cut; a subgroup that needs more gets private buffers
+constexpr int kInitialSlots = 192;
 constexpr int kUniforms = 40000;  // a call never draws more: sweeps = min(n, 40000 / reads)
 
 // std::uniform draws of std::discrete_distribution on std::mt19937(1234): generate_canonical<double,53>
@@ -63,8 +65,12 @@ struct Sub
     const FlatGraph* g = nullptr;
     int R = 0;
     // device state
-    DevBuf<double> ll, sub;
-    DevBuf<char> d_label, d_pool;
+    // device state: carved out of the engine's arenas at start (one allocation for the whole batch);
+    // only a subgroup that outgrows its slots gets private buffers
+    struct Ptr { double* p = nullptr; } ll, sub;
+    const char* d_label = nullptr;
+    const char* d_pool = nullptr;
+    DevBuf<double> ll_own, sub_own;
     int slot_cap = 0;
     std::vector<int> free_slots;
     std::vector<char> retained;
@@ -237,6 +243,8 @@ struct Engine
     DevBuf<double> d_D, d_W, d_U;
     DevBuf<InheritOp> d_ops;
     DevBuf<unsigned long long> d_counters;
+    DevBuf<double> ll_arena, sub_arena;
+    DevBuf<char> char_arena;
     long long w_total = 0, max_stride = 0;
     std::vector<cudaEvent_t> gibbs_events;  // pairs, resolved after the last step
 
@@ -258,14 +266,13 @@ struct Engine
         nsub.reserve((size_t)cap * 36);
         RAMBL_CUDA(cudaMemsetAsync(nll.p, 0, sizeof(double) * (size_t)cap * s.R, st));
         launch_init_models(nsub.p, cap, e, st, &s.local_launches);
-        if (s.slot_cap)
-        {
-            RAMBL_CUDA(cudaMemcpyAsync(nll.p, s.ll.p, sizeof(double) * (size_t)s.slot_cap * s.R, cudaMemcpyDeviceToDevice, st));
-            RAMBL_CUDA(cudaMemcpyAsync(nsub.p, s.sub.p, sizeof(double) * (size_t)s.slot_cap * 36, cudaMemcpyDeviceToDevice, st));
-        }
-        if (s.slot_cap) RAMBL_CUDA(cudaStreamSynchronize(st));  // the old buffers are freed below
-        std::swap(s.ll.p, nll.p); std::swap(s.ll.cap, nll.cap);
-        std::swap(s.sub.p, nsub.p); std::swap(s.sub.cap, nsub.cap);
+        RAMBL_CUDA(cudaMemcpyAsync(nll.p, s.ll.p, sizeof(double) * (size_t)s.slot_cap * s.R, cudaMemcpyDeviceToDevice, st));
+        RAMBL_CUDA(cudaMemcpyAsync(nsub.p, s.sub.p, sizeof(double) * (size_t)s.slot_cap * 36, cudaMemcpyDeviceToDevice, st));
+        RAMBL_CUDA(cudaStreamSynchronize(st));  // the old private buffers (if any) are freed below
+        std::swap(s.ll_own.p, nll.p); std::swap(s.ll_own.cap, nll.cap);
+        std::swap(s.sub_own.p, nsub.p); std::swap(s.sub_own.cap, nsub.cap);
+        s.ll.p = s.ll_own.p;
+        s.sub.p = s.sub_own.p;
         for (int k = cap - 1; k >= s.slot_cap; --k) s.free_slots.push_back(k);
         s.retained.resize(cap, 0);
         s.slot_cap = cap;
@@ -309,21 +316,50 @@ struct Engine
                 if (in[i].pair_off[r + 1] - in[i].pair_off[r] < in[i].read_cn[r])
                     throw Error(RAMBL_ERR_INVALID, "ReadPairs needs one entry per read copy");
             max_stride = std::max<long long>(max_stride, s.R);
-            s.d_label.reserve(std::max<size_t>(1, s.g->label_chars.size()));
-            s.d_pool.reserve(std::max<size_t>(1, s.g->pool_chars.size()));
-            if (!s.g->label_chars.empty())
-                RAMBL_CUDA(cudaMemcpyAsync(s.d_label.p, s.g->label_chars.data(), s.g->label_chars.size(), cudaMemcpyHostToDevice, st));
-            if (!s.g->pool_chars.empty())
-                RAMBL_CUDA(cudaMemcpyAsync(s.d_pool.p, s.g->pool_chars.data(), s.g->pool_chars.size(), cudaMemcpyHostToDevice, st));
-            stats.h2d_bytes += (long long)(s.g->label_chars.size() + s.g->pool_chars.size());
-            grow_slots(s, 64);  // growing later means a device allocation and a copy in the middle of the walk
             s.present.assign(s.R, 0);
+            s.slot_cap = kInitialSlots;
+            for (int k = kInitialSlots - 1; k >= 0; --k) s.free_slots.push_back(k);
+            s.retained.assign(kInitialSlots, 0);
             s.mark.assign(s.g->n_nodes, -1);
+            s.cur.assign(1, 0);
+            if (s.g->n_nodes == 0) s.done = true;
+        }
+        // one allocation per kind for the whole batch (thousands of cudaMalloc/cudaFree pairs cost seconds)
+        size_t n_ll = 0, n_sub = 0, n_ch = 0;
+        for (const Sub& s : subs)
+        {
+            n_ll += (size_t)kInitialSlots * s.R;
+            n_sub += (size_t)kInitialSlots * 36;
+            n_ch += ((s.g->label_chars.size() + 15) & ~(size_t)15) + ((s.g->pool_chars.size() + 15) & ~(size_t)15);
+        }
+        ll_arena.reserve(std::max<size_t>(n_ll, 1));
+        sub_arena.reserve(std::max<size_t>(n_sub, 1));
+        char_arena.reserve(std::max<size_t>(n_ch, 16));
+        RAMBL_CUDA(cudaMemsetAsync(ll_arena.p, 0, sizeof(double) * n_ll, st));
+        launch_init_models(sub_arena.p, (int)(n_sub / 36), e, st, &stats.launches);
+        std::vector<char> host_chars(std::max<size_t>(n_ch, 16), 0);
+        size_t o_ll = 0, o_sub = 0, o_ch = 0;
+        for (Sub& s : subs)
+        {
+            s.ll.p = ll_arena.p + o_ll;
+            s.sub.p = sub_arena.p + o_sub;
+            o_ll += (size_t)kInitialSlots * s.R;
+            o_sub += (size_t)kInitialSlots * 36;
+            s.d_label = char_arena.p + o_ch;
+            if (!s.g->label_chars.empty()) memcpy(&host_chars[o_ch], s.g->label_chars.data(), s.g->label_chars.size());
+            o_ch += (s.g->label_chars.size() + 15) & ~(size_t)15;
+            s.d_pool = char_arena.p + o_ch;
+            if (!s.g->pool_chars.empty()) memcpy(&host_chars[o_ch], s.g->pool_chars.data(), s.g->pool_chars.size());
+            o_ch += (s.g->pool_chars.size() + 15) & ~(size_t)15;
+        }
+        RAMBL_CUDA(cudaMemcpyAsync(char_arena.p, host_chars.data(), host_chars.size(), cudaMemcpyHostToDevice, st));
+        RAMBL_CUDA(cudaStreamSynchronize(st));  // host_chars goes out of scope
+        stats.h2d_bytes += (long long)host_chars.size();
+        for (Sub& s : subs)
+        {
             Cand root;  // Strain(100,e), NonparametricClustering.cpp:281
             root.slot = take_slot(s);
             s.cands.push_back(root);
-            s.cur.assign(1, 0);
-            if (s.g->n_nodes == 0) s.done = true;
         }
     }
 
@@ -578,27 +614,26 @@ struct Engine
         }
     }
 
-    // pack the private shares of the subgroups into the pinned arenas (offsets become arena offsets)
+    // pack the private shares of the subgroups into the pinned arenas (offsets become arena offsets);
+    // the offsets are a serial prefix sum, the copies run on the workers
     void pack_step()
     {
         h_groups.clear();
         group_sub.clear();
         w_total = 0;
         size_t ti = 0, td = 0;
-        for (const Sub& s : subs) if (s.has_group) { ti += s.I.size(); td += s.Dv.size(); }
-        p_I.reserve(std::max<size_t>(ti, 1));
-        p_D.reserve(std::max<size_t>(td, 1));
-        n_I = n_D = 0;
+        std::vector<size_t> at_i, at_d;
         for (size_t i = 0; i < subs.size(); ++i)
         {
             Sub& s = subs[i];
             if (!s.has_group) continue;
             StepGroup sg = s.sg;
-            const int bi = (int)n_I, bd = (int)n_D;
-            if (!s.I.empty()) memcpy(p_I.p + n_I, s.I.data(), sizeof(int) * s.I.size());
-            if (!s.Dv.empty()) memcpy(p_D.p + n_D, s.Dv.data(), sizeof(double) * s.Dv.size());
-            n_I += s.I.size();
-            n_D += s.Dv.size();
+            const int bi = (int)ti, bd = (int)td;
+            at_i.push_back(ti);
+            at_d.push_back(td);
+            ti += s.I.size();
+            td += s.Dv.size();
+            if (ti > 0x7fffffffull) throw Error(RAMBL_ERR_CAPACITY, "a level of this batch needs more than 2^31 staged integers");
             sg.slot_off += bi; sg.lab_off += bi; sg.rid_off += bi; sg.draw_off += bi;
             sg.ab_off += bd;
             sg.w_off = w_total;
@@ -610,6 +645,17 @@ struct Engine
             stats.draws += s.step_draws;
             s.has_group = false;
         }
+        n_I = ti;
+        n_D = td;
+        p_I.reserve(std::max<size_t>(ti, 1));
+        p_D.reserve(std::max<size_t>(td, 1));
+        auto copy_one = [&](size_t k) {
+            const Sub& s = subs[group_sub[k]];
+            if (!s.I.empty()) memcpy(p_I.p + at_i[k], s.I.data(), sizeof(int) * s.I.size());
+            if (!s.Dv.empty()) memcpy(p_D.p + at_d[k], s.Dv.data(), sizeof(double) * s.Dv.size());
+        };
+        if (workers && group_sub.size() >= 8) workers->run(group_sub.size(), copy_one);
+        else for (size_t k = 0; k < group_sub.size(); ++k) copy_one(k);
     }
 
     void flush_inherits()
@@ -648,8 +694,8 @@ struct Engine
             sg.ll = s.ll.p;
             sg.ll_stride = s.R;
             sg.sub = s.sub.p;
-            sg.label_chars = s.d_label.p;
-            sg.pool_chars = s.d_pool.p;
+            sg.label_chars = s.d_label;
+            sg.pool_chars = s.d_pool;
             max_S = std::max(max_S, sg.S);
             max_m = std::max(max_m, sg.m);
             max_D = std::max(max_D, sg.D);
