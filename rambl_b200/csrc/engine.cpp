@@ -42,7 +42,8 @@ std::vector<double> canonical_stream(int n)
     return u;
 }
 
-// per-group scratch in the weights buffer (layout in dpm.cu): [S][D padded to 32] + [D] + [D], kept 256-byte aligned
+// per-group scratch in the weights buffer (layout in dpm.cu): [D padded to 32 / 32][S][32] weight tiles + [D]
+// normalisers + [D] letter codes, kept 256-byte aligned
 inline long long scratch_doubles(int S, int D)
 {
     const long long Dp = (D + 31) & ~31;
@@ -64,10 +65,9 @@ struct Sub
     const SubgroupInput* in = nullptr;
     const FlatGraph* g = nullptr;
     int R = 0;
-    // device state
     // device state: carved out of the engine's arenas at start (one allocation for the whole batch);
     // only a subgroup that outgrows its slots gets private buffers
-    struct Ptr { double* p = nullptr; } ll, sub;
+    struct DevPtr { double* p = nullptr; } ll, sub;  // [slot][read] log-likelihoods, [slot][36] model counts
     const char* d_label = nullptr;
     const char* d_pool = nullptr;
     DevBuf<double> ll_own, sub_own;
