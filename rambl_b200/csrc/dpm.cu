@@ -312,10 +312,10 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
     };
     if (n_rounds > 0) stage(0, 0);
     int sweep = 0, blk = 0;
-    int top_step = 1;
-    while (top_step * 2 <= S - 1) top_step *= 2;
     const int Cs = (S + GIBBS_NW - 1) / GIBBS_NW;               // strains per chunk
     const int s_lo = min(S, warp * Cs), s_hi = min(S, s_lo + Cs);  // this warp's chunk
+    int chunk_step = 1;
+    while (chunk_step * 2 <= Cs) chunk_step *= 2;
     unsigned pass_id = 0;
     // the uniform and the read letter of a draw come from global memory: fetch them one round ahead
     double u_next = (n_rounds > 0 && lane < D) ? U[lane] : 0.0;
@@ -368,15 +368,24 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
         };
         int c;
         {
-            // lower_bound over the (non-decreasing) cumulative weights of strains 0..S-2; S-1 if none reaches u*total
+            // lower_bound of u*total over the (non-decreasing) cumulative weights of strains 0..S-2, S-1 if none
+            // reaches it -- in two levels: the chunk first (off[q] IS the cumulative weight at the end of chunk
+            // q-1, the same number, so this is the same answer), then a binary search inside that chunk only
             const double thr = u * base_tot;
-            int cn = 0;
-            for (int step = top_step; step > 0; step >>= 1)
+            int q = 0;
+#pragma unroll
+            for (int k = 1; k < GIBBS_NW; ++k) q += (off[k] < thr) ? 1 : 0;
+            double oq = 0;
+#pragma unroll
+            for (int k = 1; k < GIBBS_NW; ++k) oq = (q == k) ? off[k] : oq;
+            const int lo = q * Cs, hi = min(lo + Cs, S - 1);  // candidates lo..hi, strain S-1 only as the fallback
+            int cn = lo;
+            for (int step = chunk_step; step > 0; step >>= 1)
             {
                 const int p = cn + step;
-                if (p <= S - 1 && base(p - 1) < thr) cn = p;
+                if (p <= hi && oq + cl[(p - 1) * 32] < thr) cn = p;
             }
-            c = valid ? cn : -1;
+            c = valid ? min(cn, S - 1) : -1;
         }
         ++passes;
         // ---- settle: check every pick against the picks of the earlier lanes until nothing moves

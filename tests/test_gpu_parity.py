@@ -223,11 +223,14 @@ def test_config4_like_indel_rich_250bp_reads(n, ie, W):
     assert compare_strains(want, got) == []
 
 
-def test_config0_scale_properties():
-    """BASELINE configs[0]-like input (2k 100bp reads, 3 strains, whole 16S gene): too slow for the oracle,
-    so check what must hold at any size: deterministic, abundances normalised, every strain a ^...$ path
-    along edges of the graph, FASTA = strains above tau in abundance order."""
-    sg = synth.config_workload(0, seed=1)[0]
+@pytest.mark.parametrize("cfg", [0, 1])
+def test_full_size_properties(cfg):
+    """BASELINE configs[0] (2k 100bp reads, 3 strains) and configs[1] (20k 150bp reads, 10 strains, the bench
+    workload) at full size on the whole 16S gene: too slow for the oracle (the reference needs 13 minutes for
+    configs[1]), so check what must hold at any size: the run is deterministic, abundances are normalised,
+    every strain is a ^...$ path along edges of the graph whose letters are its consensus, FASTA = strains
+    above tau in abundance order."""
+    sg = synth.config_workload(cfg, seed=1)[0]
     b1, b2 = _solve([sg]), _solve([sg])
     assert b1.status(0) == api.RAMBL_OK
     assert b1.strains_text(0) == b2.strains_text(0)
@@ -248,3 +251,21 @@ def test_config0_scale_properties():
     # consensus sequences are full-length 16S candidates
     for k in order:
         assert abs(len(st[k].plain_seq()) - len(sg.gene)) <= 0.05 * len(sg.gene)
+    # every read's log-likelihood under every kept strain is a finite, non-positive number
+    for s in b1.strains(0, with_loglik=True):
+        assert np.all(np.isfinite(s.read_loglik)) and np.all(s.read_loglik <= 0)
+
+
+def test_config2_slice_batched_equals_sharded():
+    """A slice of configs[2] (subgroups x 5k reads): one batch of 6 subgroups gives, subgroup by subgroup, what
+    two 'ranks' of 3 give -- the multi-GPU sharding changes nothing in the results."""
+    from rambl_b200 import shard
+    sgs = [synth.make_subgroup(5000, 150, 2 + (k % 5), seed=k, window=(0, 400)) for k in range(6)]
+    whole = _solve(sgs)
+    parts = shard.assign([shard.cost_proxy(s) for s in sgs], 2)
+    assert sorted(parts[0] + parts[1]) == list(range(6))
+    for mine in parts:
+        b = _solve([sgs[i] for i in mine])
+        for local, i in enumerate(mine):
+            assert b.status(local) == whole.status(i)
+            assert b.strains_text(local) == whole.strains_text(i)
