@@ -80,6 +80,14 @@ struct GraphBuilder::Impl
     std::vector<LevelPlan> plans;
     int first_problem = 0, n_problems = 0;
     int n_reads = 0;
+    // Guard against inputs on which the reference's construction never ends (alignments that make the
+    // graph cyclic, e.g. reads that begin with a deletion): every loop below pays into one budget.
+    mutable long long work = 0;
+    void tick(const char* where) const
+    {
+        if (++work > 100000000LL + 200LL * (long long)V.size())
+            throw Error(RAMBL_ERR_INVALID, std::string("graph construction does not terminate (malformed alignments?) in ") + where);
+    }
 
     int add(uint8_t st, const std::string& label)
     {
@@ -254,6 +262,7 @@ struct GraphBuilder::Impl
         std::vector<int> todo(1, u);
         while (!todo.empty())
         {
+            tick("insertion scan");
             const int v = todo.back();
             todo.pop_back();
             const Vertex& nv = V[v];
@@ -394,6 +403,7 @@ struct GraphBuilder::Impl
         int level = 0;
         while (!cur.empty())
         {
+            tick("deletion-free levels");
             const int u = cur.back();
             cur.pop_back();
             if (first_seen[u] < 0) first_seen[u] = level;
@@ -426,6 +436,7 @@ struct GraphBuilder::Impl
         std::vector<std::pair<int, int>> todo(1, {w, 0});
         while (!todo.empty())
         {
+            tick("deletion scan");
             const int u = todo.back().first, pass = todo.back().second;
             todo.pop_back();
             const Vertex& nu = V[u];
@@ -492,6 +503,7 @@ struct GraphBuilder::Impl
         std::vector<std::pair<int, int>> plan;
         while (!todo.empty())
         {
+            tick("sibling merge");
             const int w = todo.front();
             todo.pop();
             if (merged[w]) continue;
@@ -526,12 +538,14 @@ struct GraphBuilder::Impl
         size_t head = 0;
         while (head < cur.size())
         {
+            tick("path collapse");
             const int u = cur[head++];
             if (level_size == 1 && V[u].out.size() == 1)
             {
                 int v = V[u].out[0];
                 while (V[v].out.size() == 1)
                 {
+                    tick("path collapse");
                     absorb(u, v);
                     v = V[u].out[0];
                 }
@@ -562,6 +576,7 @@ struct GraphBuilder::Impl
         mark[0] = epoch;
         while (n != N)
         {
+            tick("node levels");
             V[at].level = at_level;
             if (nxt.empty()) { level += 1; ++epoch; }
             if (!cur.empty())

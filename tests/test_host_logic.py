@@ -153,3 +153,63 @@ def test_graph_built_elsewhere_gets_the_reference_edge_counts():
     bad = api.StrainCallBatch()
     with pytest.raises(api.RamblError):
         bad.add_graph([dict(st=0, label="A", out=[1], pool=[]), dict(st=0, label="$", out=[], pool=[])], [])
+
+
+def _random_cigar_case(rnd):
+    L = rnd.randint(8, 60)
+    gene = "".join(rnd.choice("ACGT") for _ in range(L))
+    reads = []
+    for _ in range(rnd.randint(1, 25)):
+        pos = rnd.randint(0, L - 2)
+        ops, ref, seq = [], pos, []
+        for k in range(rnd.randint(1, 6)):
+            room = L - ref
+            if room <= 0:
+                break
+            op = rnd.choice("MMMMIDS=X") if k else rnd.choice("MMMMMIS=")
+            if op == "S" and k != 0:
+                op = "M"
+            n = rnd.randint(1, 5)
+            if op in "M=X":
+                n = min(n, room)
+                seq += [gene[ref + q] if rnd.random() < 0.8 else rnd.choice("ACGT") for q in range(n)]
+                ref += n
+            elif op == "D":
+                n = min(n, room)
+                ref += n
+            else:  # I, S
+                seq += [rnd.choice("ACGT") for _ in range(n)]
+            ops.append("%d%s" % (n, op))
+        if ops:
+            reads.append((pos, "".join(ops), "".join(seq), rnd.randint(1, 3)))
+    return gene, reads
+
+
+def test_random_cigars_match_oracle_or_are_refused():
+    """Arbitrary CIGAR shapes (reads that begin with an insertion, end in a deletion, stacked indels, clips,
+    =/X): the product builds the oracle's graph, or refuses the input with RAMBL_ERR_INVALID -- including the
+    alignments on which the reference's construction never returns (a budget on the construction loops)."""
+    import random
+    import signal
+    rnd = random.Random(2)
+    refused = 0
+    for _ in range(250):
+        gene, reads = _random_cigar_case(rnd)
+        if not reads:
+            continue
+        pos, cig, seq, cn = zip(*reads)
+        b = api.StrainCallBatch()
+        b.add_subgroup(gene, pos, cig, seq, cn)
+        try:
+            b.thread_reads()
+            b.finish_graphs_with_rows([refpy.msa_align(p, "oracle") for p in b.msa_problems()])
+        except api.RamblError as e:
+            assert e.code == api.RAMBL_ERR_INVALID
+            refused += 1
+            continue
+        signal.alarm(60)  # the oracle has no such budget
+        o = refpy.RefPog(gene, pos, cig, seq, cn, variant="oracle")
+        signal.alarm(0)
+        assert strip_sib(b.graph_dump(0)) == strip_sib(o.dump()), (gene, reads)
+        assert b.output_edge(0) == o.edges()
+    assert refused < 125
