@@ -54,6 +54,9 @@ typedef struct rambl_stats
 const char* rambl_last_error(void);
 int rambl_device_count(void);
 void rambl_free(void* p); /* for every char* this library returns */
+/* Device and pinned-host buffers are cached between calls (cudaMalloc/cudaFree cost up to a second per
+ * strain search); this returns the cached blocks to the driver. */
+void rambl_release_cached_memory(void);
 
 /* ---- MultipleSequenceAlignmentSP<Index2D,SimpleScoreModel,vector,string,char>::align
  *      (MultipleSequenceAlignment.hpp:87-107, MultipleSequenceAlignmentSP.cpp:10-301), batched.

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <chrono>
 #include <sstream>
 #include <thread>
 #include <atomic>
@@ -207,6 +208,8 @@ int rambl_device_count(void)
 }
 
 void rambl_free(void* p) { free(p); }
+
+void rambl_release_cached_memory(void) { release_cached_memory(); }
 
 int64_t rambl_msa_rows_capacity(int32_t P, const int32_t* prob_seq_off, const int32_t* seq_off)
 {
@@ -441,7 +444,11 @@ int rambl_batch_infer(rambl_batch* b, int32_t n, float e, float tau, float diff,
         prm.n = n; prm.e = e; prm.tau = tau; prm.diff = diff; prm.assign = do_assign != 0; prm.keep_loglik = keep_loglik != 0;
         std::vector<SubgroupResult> out;
         EngineStats es;
+        const auto w0 = std::chrono::steady_clock::now();
         infer_batch(in, prm, out, es);
+        if (getenv("RAMBL_TRACE"))
+            fprintf(stderr, "[rambl] rambl_batch_infer: infer_batch returned after %.1f ms\n",
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count());
         for (size_t i = 0; i < out.size(); ++i) { b->subs[i]->result = std::move(out[i]); b->subs[i]->inferred = true; }
         b->stats.gpu_launches += es.launches;
         b->stats.level_steps += es.level_steps;

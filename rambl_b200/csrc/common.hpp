@@ -4,6 +4,7 @@
 
 #include "rambl_b200.h"
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -27,33 +28,45 @@ struct Error : std::runtime_error
             throw ::rambl::Error(RAMBL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+// Device and pinned-host memory come from a process-wide cache: cudaMalloc / cudaFree / cudaMallocHost /
+// cudaFreeHost synchronise the device and cost from tens of microseconds to a second (teardown of one
+// strain search was measured at up to 1.3 s), so buffers released by one call are handed to the next
+// instead of going back to the driver.  Sizes are rounded up to a power of two.  rambl_release_cached_memory()
+// (C ABI) returns everything to the driver.
+void* cached_device_alloc(size_t bytes, size_t* granted);
+void cached_device_free(void* p, size_t granted);
+void* cached_pinned_alloc(size_t bytes, size_t* granted);
+void cached_pinned_free(void* p, size_t granted);
+void release_cached_memory();
+
 // A device buffer that only grows; reused across launches so the level loop does not malloc.
 template <typename T>
 struct DevBuf
 {
     T* p = nullptr;
-    size_t cap = 0;
+    size_t cap = 0;      // elements
+    size_t bytes = 0;    // granted by the cache
     DevBuf() {}
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
-    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap), bytes(o.bytes) { o.p = nullptr; o.cap = 0; o.bytes = 0; }
+    ~DevBuf() { if (p) cached_device_free(p, bytes); }
+    void swap(DevBuf& o) { std::swap(p, o.p); std::swap(cap, o.cap); std::swap(bytes, o.bytes); }
     // grows (contents are NOT kept unless keep=true)
     void reserve(size_t n, bool keep = false, cudaStream_t st = 0)
     {
         if (n <= cap) return;
-        size_t ncap = cap ? cap : 256;
-        while (ncap < n) ncap *= 2;
-        T* q = nullptr;
-        RAMBL_CUDA(cudaMalloc(&q, ncap * sizeof(T)));
+        size_t granted = 0;
+        T* q = static_cast<T*>(cached_device_alloc(std::max<size_t>(n, 64) * sizeof(T), &granted));
         if (keep && p && cap)
         {
             RAMBL_CUDA(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
             RAMBL_CUDA(cudaStreamSynchronize(st));
         }
-        if (p) cudaFree(p);
+        if (p) cached_device_free(p, bytes);
         p = q;
-        cap = ncap;
+        bytes = granted;
+        cap = granted / sizeof(T);
     }
 };
 
@@ -63,20 +76,20 @@ struct PinBuf
 {
     T* p = nullptr;
     size_t cap = 0;
+    size_t bytes = 0;
     PinBuf() {}
     PinBuf(const PinBuf&) = delete;
     PinBuf& operator=(const PinBuf&) = delete;
-    ~PinBuf() { if (p) cudaFreeHost(p); }
+    ~PinBuf() { if (p) cached_pinned_free(p, bytes); }
     void reserve(size_t n)
     {
         if (n <= cap) return;
-        size_t ncap = cap ? cap : 256;
-        while (ncap < n) ncap *= 2;
-        T* q = nullptr;
-        RAMBL_CUDA(cudaMallocHost(&q, ncap * sizeof(T)));
-        if (p) cudaFreeHost(p);
+        size_t granted = 0;
+        T* q = static_cast<T*>(cached_pinned_alloc(std::max<size_t>(n, 64) * sizeof(T), &granted));
+        if (p) cached_pinned_free(p, bytes);
         p = q;
-        cap = ncap;
+        bytes = granted;
+        cap = granted / sizeof(T);
     }
 };
 

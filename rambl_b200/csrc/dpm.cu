@@ -389,6 +389,7 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
         }
         ++passes;
         // ---- settle: check every pick against the picks of the earlier lanes until nothing moves
+        int settle_passes = 0;
         for (;;)
         {
             double* pbuf = part + (size_t)(pass_id & 1) * 3 * GIBBS_NW * 32;
@@ -454,8 +455,9 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
                 }
             }
             ++passes;
-            // every warp holds the same picks and reaches the same verdict
-            if (!__any_sync(full, !ok)) break;
+            // every warp holds the same picks and reaches the same verdict; lane j is final after j+1 passes, so
+            // 33 passes always suffice -- the cap only guards the device against a non-terminating launch
+            if (!__any_sync(full, !ok) || ++settle_passes > 40) break;
             __syncthreads();  // picks[] is rewritten by the next pass
         }
         ++rounds;

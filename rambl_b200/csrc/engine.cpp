@@ -269,8 +269,8 @@ struct Engine
         RAMBL_CUDA(cudaMemcpyAsync(nll.p, s.ll.p, sizeof(double) * (size_t)s.slot_cap * s.R, cudaMemcpyDeviceToDevice, st));
         RAMBL_CUDA(cudaMemcpyAsync(nsub.p, s.sub.p, sizeof(double) * (size_t)s.slot_cap * 36, cudaMemcpyDeviceToDevice, st));
         RAMBL_CUDA(cudaStreamSynchronize(st));  // the old private buffers (if any) are freed below
-        std::swap(s.ll_own.p, nll.p); std::swap(s.ll_own.cap, nll.cap);
-        std::swap(s.sub_own.p, nsub.p); std::swap(s.sub_own.cap, nsub.cap);
+        s.ll_own.swap(nll);
+        s.sub_own.swap(nsub);
         s.ll.p = s.ll_own.p;
         s.sub.p = s.sub_own.p;
         for (int k = cap - 1; k >= s.slot_cap; --k) s.free_slots.push_back(k);
@@ -838,12 +838,15 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
     require_device();
     out.assign(in.size(), SubgroupResult());
     if (in.empty()) return;
+    const auto w0 = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     Engine E(prm, stream, stats);
     cudaEvent_t e0, e1;
     RAMBL_CUDA(cudaEventCreate(&e0));
     RAMBL_CUDA(cudaEventCreate(&e1));
     RAMBL_CUDA(cudaEventRecord(e0, stream));
     E.start(in);
+    const double ms_start = since(w0);
     {
         unsigned nt = std::thread::hardware_concurrency();
         nt = std::min<unsigned>(nt ? nt : 1, 32);
@@ -892,9 +895,11 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
                 for (size_t k = 0; k < s.result.size(); ++k) s.result[k].ab = al[s.ab_off + k];
     }
     else E.flush_inherits();
+    const double ms_walk = since(w0);
     RAMBL_CUDA(cudaEventRecord(e1, stream));
     RAMBL_CUDA(cudaStreamSynchronize(stream));
     E.collect_kernel_times();
+    const double ms_times = since(w0);
     // ---- gather
     for (size_t i = 0; i < E.subs.size(); ++i)
     {
@@ -935,6 +940,9 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
     stats.gpu_ms += ms;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    if (getenv("RAMBL_TRACE"))
+        fprintf(stderr, "[rambl] infer wall ms: start %.1f, walk+assign until %.1f, kernel times until %.1f, gather until %.1f\n",
+                ms_start, ms_walk, ms_times, since(w0));
 }
 
 }  // namespace rambl

@@ -1,0 +1,99 @@
+// Process-wide cache of device and pinned-host allocations (see common.hpp).
+#include <map>
+#include <mutex>
+
+#include "common.hpp"
+
+namespace rambl {
+
+namespace {
+struct Cache
+{
+    std::mutex mu;
+    std::multimap<size_t, void*> device, pinned;  // granted size -> free block
+};
+Cache& cache()
+{
+    static Cache* c = new Cache;  // never destroyed: blocks may be released after main() returns
+    return *c;
+}
+size_t round_up(size_t bytes)
+{
+    size_t g = 256;
+    while (g < bytes) g <<= 1;
+    return g;
+}
+}  // namespace
+
+void* cached_device_alloc(size_t bytes, size_t* granted)
+{
+    const size_t g = round_up(bytes);
+    *granted = g;
+    {
+        std::lock_guard<std::mutex> lk(cache().mu);
+        auto it = cache().device.find(g);
+        if (it != cache().device.end())
+        {
+            void* p = it->second;
+            cache().device.erase(it);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, g);
+    if (e != cudaSuccess)
+    {   // give the driver back what we hold and try once more
+        release_cached_memory();
+        e = cudaMalloc(&p, g);
+    }
+    if (e != cudaSuccess) throw Error(RAMBL_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return p;
+}
+
+void cached_device_free(void* p, size_t granted)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(cache().mu);
+    cache().device.insert({granted, p});
+}
+
+void* cached_pinned_alloc(size_t bytes, size_t* granted)
+{
+    const size_t g = round_up(bytes);
+    *granted = g;
+    {
+        std::lock_guard<std::mutex> lk(cache().mu);
+        auto it = cache().pinned.find(g);
+        if (it != cache().pinned.end())
+        {
+            void* p = it->second;
+            cache().pinned.erase(it);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, g);
+    if (e != cudaSuccess) throw Error(RAMBL_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    return p;
+}
+
+void cached_pinned_free(void* p, size_t granted)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(cache().mu);
+    cache().pinned.insert({granted, p});
+}
+
+void release_cached_memory()
+{
+    std::multimap<size_t, void*> d, h;
+    {
+        std::lock_guard<std::mutex> lk(cache().mu);
+        d.swap(cache().device);
+        h.swap(cache().pinned);
+    }
+    for (auto& kv : d) cudaFree(kv.second);
+    for (auto& kv : h) cudaFreeHost(kv.second);
+}
+
+}  // namespace rambl
