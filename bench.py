@@ -172,7 +172,13 @@ def run_reference_arm(args, rank, world):
         return
     import multiprocessing as mp
     cores = max(1, min(os.cpu_count() or 1, 64))
-    window = args.ref_sample_window
+    # bounded: the largest sample window whose K timed steps fit in about 2.5 minutes (seconds per step per core,
+    # measured with oracle/_ref -O2: 200bp ~50 s, 160bp ~16 s, 100bp ~11 s, 60bp ~5 s)
+    window = 60
+    for w, est in ((args.ref_sample_window, 50.0), (160, 16.0), (100, 11.0)):
+        if w <= args.ref_sample_window and args.steps * est <= 150.0:
+            window = w
+            break
     ctx = mp.get_context("spawn")
     times = []
     reads = 0
