@@ -223,6 +223,24 @@ def test_config4_like_indel_rich_250bp_reads(n, ie, W):
     assert compare_strains(want, got) == []
 
 
+def test_depth800_sample_of_configs1_matches_reference():
+    """The bounded sample bench.py times the reference on (configs[1] restricted to a 160 bp window: depth 800,
+    150 bp reads, 10 strains, ~840 reads, 50 sweeps of ~800 draws per level) -- the deepest case the reference
+    finishes in seconds.  Strain paths, order, consensus and abundances against the real reference when
+    oracle/_ref is present (else the oracle)."""
+    import bench
+    sg = bench.make_cpu_sample(160, 0)
+    variant = "" if refpy.available("") else "oracle"
+    o = refpy.RefPog(sg.gene, sg.pos, sg.cigar, sg.seq, sg.cn, variant=variant)
+    want, _ = o.infer(sg.pair_off, sg.pair_val)
+    b = _solve([sg])
+    assert b.status(0) == api.RAMBL_OK
+    assert b.output_edge(0) == o.edges()
+    got = refpy.parse_strain_dump(b.strains_text(0))
+    assert compare_strains(want, got) == []
+    assert b.stats()["draws"] > 1000000
+
+
 @pytest.mark.parametrize("cfg", [0, 1])
 def test_full_size_properties(cfg):
     """BASELINE configs[0] (2k 100bp reads, 3 strains) and configs[1] (20k 150bp reads, 10 strains, the bench
