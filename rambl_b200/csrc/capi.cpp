@@ -9,6 +9,7 @@
 #include <thread>
 #include <atomic>
 
+#include "dpm.cuh"
 #include "engine.hpp"
 #include "msa_sp.hpp"
 #include "pog.hpp"
@@ -210,6 +211,13 @@ int rambl_device_count(void)
 void rambl_free(void* p) { free(p); }
 
 void rambl_release_cached_memory(void) { release_cached_memory(); }
+
+int rambl_set_gibbs_blocks(int32_t blocks)
+{
+    if (blocks != 0 && blocks != 1 && blocks != 2 && blocks != 4) return RAMBL_ERR_INVALID;
+    set_gibbs_blocks(blocks);
+    return RAMBL_OK;
+}
 
 int64_t rambl_msa_rows_capacity(int32_t P, const int32_t* prob_seq_off, const int32_t* seq_off)
 {

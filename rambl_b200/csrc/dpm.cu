@@ -269,45 +269,70 @@ __global__ void __launch_bounds__(256) k_hard(const StepGroup* __restrict__ grou
 // cumulative weight stays non-decreasing in s.
 // The weights of a round are one contiguous S x 32 tile, bulk-copied (TMA, no tensor map) into a
 // double-buffered shared tile while the previous round is being settled.
-constexpr int GIBBS_NW = 4;
+constexpr int GIBBS_NW = 4;             // warps per 32-draw block
 constexpr int GIBBS_L = 32 / GIBBS_NW;  // source lanes per warp in the gather
 
-__global__ void __launch_bounds__(32 * GIBBS_NW, 1)
+// A wide launch (NG > 1) takes NG blocks of 32 draws per round, block b on warps 4b..4b+3.  Inside a block
+// nothing changes.  Across blocks the same speculation applies one level up: the draws of block b see every
+// pick of the blocks before it as a per-strain count h_b[s] (one byte per block, packed in a word per strain),
+//     corr_j(s) += sum_{s' <= s} h_b[s'] * w_j[s']
+// evaluated over the warp's strain chunk, where only a handful of strains have a non-zero count.  All blocks
+// check at once against the picks currently published; draw 32b+j is final once every earlier draw is, so the
+// fixed point is still the sequential chain.  Masses move by 1 in hundreds to tens of thousands, so a round of
+// 128 draws settles in two passes most of the time as well.  A round's weights are NG consecutive tiles: still
+// one bulk copy.  Shared memory grows with NG, so the launcher picks NG by strain count and by how many
+// subgroups share the machine (a batch of hundreds fills the SMs with narrow CTAs instead).
+__device__ __forceinline__ void group_bar(int grp)
+{
+    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+}
+
+template <int NG>
+__global__ void __launch_bounds__(128 * NG, 1)
 k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double* __restrict__ Dar,
         double* __restrict__ W, const double* __restrict__ U, unsigned long long* counters, int smem_S)
 {
     const StepGroup g = groups[blockIdx.x];
     if (g.mode != MODE_GIBBS && g.mode != MODE_ASSIGN) return;
     extern __shared__ __align__(128) double gibbs_smem[];  // sized for the largest S of the launch (smem_S)
-    double* wbuf = gibbs_smem;                       // [2][strain][lane] weights of a round's 32 draws (bulk-copied)
-    double* cumbuf = wbuf + 2 * smem_S * 32;         // [strain][lane] prefix sums inside the strain chunk
-    double* mass = cumbuf + smem_S * 32;             // [smem_S]
-    double* ctot = mass + smem_S;                    // [GIBBS_NW][lane] chunk totals
-    double* part = ctot + GIBBS_NW * 32;             // [2][3][GIBBS_NW][lane] partial gather sums, double-buffered by pass
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(part + 2 * 3 * GIBBS_NW * 32);  // [2]
-    int* cnt = reinterpret_cast<int*>(bars + 2);     // [smem_S][8]
-    int* hist = cnt + smem_S * 8;                    // [smem_S]
-    int* picks = hist + smem_S;                      // [32]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, S = g.S, D = g.D;
+    double* wbuf = gibbs_smem;                       // [2][block][strain][lane] weights of a round (bulk-copied)
+    double* cumbuf = wbuf + 2 * NG * smem_S * 32;    // [block][strain][lane] prefix sums inside the strain chunk
+    double* mass = cumbuf + NG * smem_S * 32;        // [smem_S] masses at the start of the round
+    double* mass0 = mass + smem_S;                   // [smem_S] masses at the start of the launch
+    double* ctot = mass0 + smem_S;                   // [block][GIBBS_NW][lane] chunk totals
+    double* part = ctot + NG * GIBBS_NW * 32;        // [3][block][GIBBS_NW][lane] partial correction sums
+    double* redo = part + 3 * NG * GIBBS_NW * 32;    // [block][GIBBS_NW][lane] the same partials while a pick is re-derived
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(redo + NG * GIBBS_NW * 32);  // [2]
+    unsigned* hpack = reinterpret_cast<unsigned*>(bars + 2);  // [smem_S] picks per strain in this round, byte b = block b
+    int* tcount = reinterpret_cast<int*>(hpack + smem_S);     // [smem_S] picks per strain since the launch began
+    int* cnt = tcount + smem_S;                      // [smem_S][8]
+    const int tid = threadIdx.x, lane = tid & 31, warp = (tid >> 5) & (GIBBS_NW - 1), grp = tid >> 7;
+    const int S = g.S, D = g.D;
     const unsigned full = 0xffffffffu;
     const double* wt = group_weights(W, g);
     const int* code = group_codes(W, g);
     const int Dp = padded_draws(D);
     for (int k = tid; k < S * 8; k += blockDim.x) cnt[k] = 0;
-    for (int s = tid; s < S; s += blockDim.x) { mass[s] = Dar[g.ab_off + s]; hist[s] = 0; }
+    for (int s = tid; s < S; s += blockDim.x)
+    {
+        const double a = Dar[g.ab_off + s];
+        mass[s] = a; mass0[s] = a; hpack[s] = 0; tcount[s] = 0;
+    }
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    const int per_sweep = Dp / 32;
+    const int tiles = Dp / 32;                       // tiles of 32 draws per sweep
+    const int per_sweep = (tiles + NG - 1) / NG;     // rounds per sweep (the last one may be short of blocks)
     const long long n_rounds = (S >= 2) ? (long long)g.nsweeps * per_sweep : 0;
     unsigned long long rounds = 0, passes = 0;
-    // stage the weights of round r: one tile of S x 32 draws, S*256 contiguous bytes, one bulk copy
+    // stage the weights of a round: its tiles are contiguous, S*256 bytes each -- one bulk copy
     auto stage = [&](long long r, int blk) {
         if (tid == 0)
         {
             const int b = (int)(r & 1);
-            mbar_expect_tx(&bars[b], (unsigned)S * 256u);
-            bulk_g2s(wbuf + (size_t)b * smem_S * 32, wt + (long long)blk * S * 32, (unsigned)S * 256u, &bars[b]);
+            const unsigned bytes = (unsigned)min(NG, tiles - blk * NG) * (unsigned)S * 256u;
+            mbar_expect_tx(&bars[b], bytes);
+            bulk_g2s(wbuf + (size_t)b * NG * smem_S * 32, wt + (long long)blk * NG * S * 32, bytes, &bars[b]);
         }
     };
     if (n_rounds > 0) stage(0, 0);
@@ -316,49 +341,45 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
     const int s_lo = min(S, warp * Cs), s_hi = min(S, s_lo + Cs);  // this warp's chunk
     int chunk_step = 1;
     while (chunk_step * 2 <= Cs) chunk_step *= 2;
-    unsigned pass_id = 0;
+    const unsigned below = (NG > 1) ? ((1u << (8 * grp)) - 1u) : 0u;  // the bytes of hpack that count for this block
+    unsigned char* hbytes = reinterpret_cast<unsigned char*>(hpack);
     // the uniform and the read letter of a draw come from global memory: fetch them one round ahead
-    double u_next = (n_rounds > 0 && lane < D) ? U[lane] : 0.0;
-    int cd_next = (n_rounds > 0 && lane < D && g.mode == MODE_GIBBS) ? code[lane] : 0;
+    double u_next = 0.0;
+    int cd_next = 0;
+    if (n_rounds > 0)
+    {
+        const int d0 = grp * 32 + lane;
+        if (grp < tiles && d0 < D)
+        {
+            u_next = U[d0];
+            if (g.mode == MODE_GIBBS) cd_next = code[d0];
+        }
+    }
     for (long long r = 0; r < n_rounds; ++r)
     {
-        const int d = blk * 32 + lane;
-        const bool valid = d < D;
+        const bool active = grp < tiles - blk * NG;  // a short last round leaves the high blocks idle
+        const int d = (blk * NG + grp) * 32 + lane;
+        const bool valid = active && d < D;
         const double u = u_next;
         const int cd = cd_next;
         const int blk_next = (blk + 1 == per_sweep) ? 0 : blk + 1;
         if (r + 1 < n_rounds)
         {
             stage(r + 1, blk_next);  // overlaps this round's arithmetic
-            const int dn = blk_next * 32 + lane;
+            const int dn = (blk_next * NG + grp) * 32 + lane;
             const int sweep_n = sweep + (blk_next == 0 ? 1 : 0);
-            u_next = (dn < D) ? U[(long long)sweep_n * D + dn] : 0.0;
-            cd_next = (dn < D && g.mode == MODE_GIBBS) ? code[dn] : 0;
+            const bool vn = grp < tiles - blk_next * NG && dn < D;
+            u_next = vn ? U[(long long)sweep_n * D + dn] : 0.0;
+            cd_next = (vn && g.mode == MODE_GIBBS) ? code[dn] : 0;
         }
         mbar_wait(&bars[r & 1], (unsigned)((r >> 1) & 1));
-        const double* wl = wbuf + (size_t)(r & 1) * smem_S * 32 + lane;
-        double* cl = cumbuf + lane;
-        // ---- pass 1: prefix sums of mass * weight over this warp's strain chunk, in strain order
-        {
-            double cum = 0;
-            int s = s_lo;
-            for (; s + 4 <= s_hi; s += 4)
-            {
-                double m4[4], w4[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { m4[q] = mass[s + q]; w4[q] = wl[(s + q) * 32]; }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { cum = fma(m4[q], w4[q], cum); cl[(s + q) * 32] = cum; }
-            }
-            for (; s < s_hi; ++s) { cum = fma(mass[s], wl[s * 32], cum); cl[s * 32] = cum; }
-            ctot[warp * 32 + lane] = cum;
-        }
-        __syncthreads();
+        const double* wl = wbuf + ((size_t)(r & 1) * NG * smem_S + (size_t)grp * S) * 32 + lane;
+        double* cl = cumbuf + (size_t)grp * smem_S * 32 + lane;
+        double* ct = ctot + grp * GIBBS_NW * 32 + lane;
+        double* pb = part + grp * GIBBS_NW * 32 + lane;  // + (which * NG * GIBBS_NW + warp) * 32
+        double* rd = redo + grp * GIBBS_NW * 32 + lane;  // + warp * 32
         double off[GIBBS_NW + 1];
         off[0] = 0;
-#pragma unroll
-        for (int q = 0; q < GIBBS_NW; ++q) off[q + 1] = off[q] + ctot[q * 32 + lane];
-        const double base_tot = off[GIBBS_NW];
         // base(s) = offset of the chunk of s + prefix sum inside the chunk
         auto base = [&](int s) {
             double o = 0;
@@ -366,8 +387,29 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
             for (int q = 1; q < GIBBS_NW; ++q) o = (s >= q * Cs) ? off[q] : o;
             return o + cl[s * 32];
         };
-        int c;
+        double base_tot = 0;
+        int c = -1;
+        if (active)
         {
+            // ---- pass 1: prefix sums of mass * weight over this warp's strain chunk, in strain order
+            {
+                double cum = 0;
+                int s = s_lo;
+                for (; s + 4 <= s_hi; s += 4)
+                {
+                    double m4[4], w4[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { m4[q] = mass[s + q]; w4[q] = wl[(s + q) * 32]; }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { cum = fma(m4[q], w4[q], cum); cl[(s + q) * 32] = cum; }
+                }
+                for (; s < s_hi; ++s) { cum = fma(mass[s], wl[s * 32], cum); cl[s * 32] = cum; }
+                ct[warp * 32] = cum;
+            }
+            group_bar(grp);
+#pragma unroll
+            for (int q = 0; q < GIBBS_NW; ++q) off[q + 1] = off[q] + ct[q * 32];
+            base_tot = off[GIBBS_NW];
             // lower_bound of u*total over the (non-decreasing) cumulative weights of strains 0..S-2, S-1 if none
             // reaches it -- in two levels: the chunk first (off[q] IS the cumulative weight at the end of chunk
             // q-1, the same number, so this is the same answer), then a binary search inside that chunk only
@@ -388,15 +430,27 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
             c = valid ? min(cn, S - 1) : -1;
         }
         ++passes;
-        // ---- settle: check every pick against the picks of the earlier lanes until nothing moves
+        // ---- settle: check every pick against the picks of the earlier draws until nothing moves
         int settle_passes = 0;
+        int c_pub = -1;  // what this lane has in hpack (warp 0 of a block keeps it)
         for (;;)
         {
-            double* pbuf = part + (size_t)(pass_id & 1) * 3 * GIBBS_NW * 32;
-            ++pass_id;
-            if (warp == 0) picks[lane] = c;  // the rare re-derivation below reads them from shared memory
+            if (NG > 1)
             {
-                // this warp gathers source lanes [warp*L, warp*L + L): picks, then weights, then sums
+                if (active && warp == 0)
+                {
+                    if (c_pub >= 0) hbytes[c_pub * 4 + grp] = 0;
+                    __syncwarp();
+                    const unsigned same = __match_any_sync(full, c);
+                    if (c >= 0 && lane == __ffs(same) - 1) hbytes[c * 4 + grp] = (unsigned char)__popc(same);
+                    c_pub = c;
+                }
+                __syncthreads();
+            }
+            bool moved = false;
+            if (active)
+            {
+                // this warp gathers source lanes [warp*L, warp*L + L) of its block: picks, then weights, then sums
                 int ci[GIBBS_L];
                 double wi[GIBBS_L];
 #pragma unroll
@@ -413,63 +467,126 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
                     p_here = fma(wi[i], (live && ci[i] <= c) ? 1.0 : 0.0, p_here);
                     p_prev = fma(wi[i], (live && ci[i] < c) ? 1.0 : 0.0, p_prev);
                 }
-                pbuf[(0 * GIBBS_NW + warp) * 32 + lane] = p_tot;
-                pbuf[(1 * GIBBS_NW + warp) * 32 + lane] = p_here;
-                pbuf[(2 * GIBBS_NW + warp) * 32 + lane] = p_prev;
-            }
-            __syncthreads();
-            double tot = 0, le_here = 0, le_prev = 0;  // corr(S-1), corr(c), corr(c-1): chunk partials added in order
-#pragma unroll
-            for (int q = 0; q < GIBBS_NW; ++q)
-            {
-                tot += pbuf[(0 * GIBBS_NW + q) * 32 + lane];
-                le_here += pbuf[(1 * GIBBS_NW + q) * 32 + lane];
-                le_prev += pbuf[(2 * GIBBS_NW + q) * 32 + lane];
-            }
-            bool ok = true;
-            if (valid)
-            {
-                const double thr = u * (base_tot + tot);
-                const bool lo_ok = (c == 0) || (base(c - 1) + le_prev < thr);
-                const bool hi_ok = (c == S - 1) || !(base(c) + le_here < thr);
-                ok = lo_ok && hi_ok;
-                if (!ok)
-                {   // rare: walk the strains with the same definition of the cumulative weight
-                    int cn = 0;
-                    for (int s = 0; s < S - 1; ++s)
+                if (NG > 1 && grp > 0)
+                {   // the picks of the earlier blocks, as counts over this warp's strain chunk (uniform branch)
+                    for (int s = s_lo; s < s_hi; ++s)
                     {
-                        double corr = 0;
-                        for (int q = 0; q < GIBBS_NW; ++q)
+                        const unsigned hp = hpack[s] & below;
+                        if (hp)
                         {
-                            double p = 0;
-                            for (int i = q * GIBBS_L; i < (q + 1) * GIBBS_L && i < lane; ++i)
-                            {
-                                const int ci = picks[i];
-                                if (ci >= 0 && ci <= s) p += wl[ci * 32];
-                            }
-                            corr += p;
+                            const double h = (double)__dp4a(hp, 0x01010101u, 0u);
+                            const double w = wl[s * 32];
+                            p_tot = fma(w, h, p_tot);
+                            p_here = fma(w, (s <= c) ? h : 0.0, p_here);
+                            p_prev = fma(w, (s < c) ? h : 0.0, p_prev);
                         }
-                        if (base(s) + corr < thr) ++cn; else break;
                     }
-                    c = cn;
+                }
+                pb[(0 * NG * GIBBS_NW + warp) * 32] = p_tot;
+                pb[(1 * NG * GIBBS_NW + warp) * 32] = p_here;
+                pb[(2 * NG * GIBBS_NW + warp) * 32] = p_prev;
+                group_bar(grp);
+                double tot = 0, le_here = 0, le_prev = 0;  // corr(S-1), corr(c), corr(c-1): chunk partials added in order
+#pragma unroll
+                for (int q = 0; q < GIBBS_NW; ++q)
+                {
+                    tot += pb[(0 * NG * GIBBS_NW + q) * 32];
+                    le_here += pb[(1 * NG * GIBBS_NW + q) * 32];
+                    le_prev += pb[(2 * NG * GIBBS_NW + q) * 32];
+                }
+                const double thr = u * (base_tot + tot);
+                bool ok = true;
+                if (valid)
+                {
+                    const bool lo_ok = (c == 0) || (base(c - 1) + le_prev < thr);
+                    const bool hi_ok = (c == S - 1) || !(base(c) + le_here < thr);
+                    ok = lo_ok && hi_ok;
+                }
+                // A pick that fails its check is re-derived by the whole block, 32 candidate strains at a time
+                // (candidate s on lane s%32 of every warp), with the SAME chunk-wise sums the check uses: warp q
+                // adds its source lanes and then its strain chunk, the four partials are added in order.  The four
+                // warps hold identical values, so they agree on who failed and take the barriers together.
+                unsigned failed = __ballot_sync(full, !ok);
+                while (failed)
+                {
+                    const int f = __ffs(failed) - 1;
+                    failed &= failed - 1;
+                    const double thr_f = __shfl_sync(full, thr, f);
+                    double off_f[GIBBS_NW];
+#pragma unroll
+                    for (int q = 1; q < GIBBS_NW; ++q) off_f[q] = __shfl_sync(full, off[q], f);
+                    const double* wf = wl - lane + f;  // the weights of draw f
+                    double wv[GIBBS_L];
+#pragma unroll
+                    for (int i = 0; i < GIBBS_L; ++i) wv[i] = wf[max(ci[i], 0) * 32];
+                    int cn = S - 1;
+                    for (int s0 = 0; s0 < S - 1; s0 += 32)
+                    {
+                        const int s = s0 + lane;
+                        double p = 0;
+#pragma unroll
+                        for (int i = 0; i < GIBBS_L; ++i)
+                        {
+                            const bool live = (warp * GIBBS_L + i < f) && (ci[i] >= 0) && (ci[i] <= s);
+                            p = fma(wv[i], live ? 1.0 : 0.0, p);
+                        }
+                        if (NG > 1 && grp > 0)
+                        {
+                            for (int t = s_lo; t < s_hi; ++t)
+                            {
+                                const unsigned hp = hpack[t] & below;
+                                if (hp) p = fma(wf[t * 32], (t <= s) ? (double)__dp4a(hp, 0x01010101u, 0u) : 0.0, p);
+                            }
+                        }
+                        rd[warp * 32] = p;
+                        group_bar(grp);
+                        double corr = 0;
+#pragma unroll
+                        for (int q = 0; q < GIBBS_NW; ++q) corr += rd[q * 32];
+                        double o = 0;
+#pragma unroll
+                        for (int q = 1; q < GIBBS_NW; ++q) o = (s >= q * Cs) ? off_f[q] : o;
+                        // strain S-1 is the fallback of the lower bound: it and the padding lanes count as "reached"
+                        const bool reached = (s >= S - 1) || !((o + cl[min(s, S - 1) * 32 - lane + f]) + corr < thr_f);
+                        const unsigned hit = __ballot_sync(full, reached);
+                        group_bar(grp);  // rd is rewritten by the next window
+                        if (hit) { cn = min(s0 + __ffs(hit) - 1, S - 1); break; }
+                    }
+                    if (lane == f)
+                    {
+                        moved = moved || (cn != c);
+                        c = cn;
+                    }
                 }
             }
             ++passes;
-            // every warp holds the same picks and reaches the same verdict; lane j is final after j+1 passes, so
-            // 33 passes always suffice -- the cap only guards the device against a non-terminating launch
-            if (!__any_sync(full, !ok) || ++settle_passes > 40) break;
-            __syncthreads();  // picks[] is rewritten by the next pass
+            // draw 32b+j is final after 32b+j+1 passes, so 32*NG+1 passes always suffice -- the cap only guards
+            // the device against a launch that does not terminate
+            const int any_moved = __syncthreads_or(moved ? 1 : 0);  // also orders this pass before the next publication
+            if (!any_moved || ++settle_passes > 32 * NG + 8) break;
         }
         ++rounds;
-        if (warp == 0)
+        // ---- commit: letter statistics, then the masses of the next round from the exact pick counts
+        if (valid && warp == 0 && g.mode == MODE_GIBBS) atomicAdd(&cnt[c * 8 + cd], 1);
+        if (NG > 1)
         {
-            if (valid)
+            for (int s = tid; s < S; s += blockDim.x)
             {
-                atomicAdd(&hist[c], 1);
-                if (g.mode == MODE_GIBBS) atomicAdd(&cnt[c * 8 + cd], 1);
+                const unsigned hp = hpack[s];
+                if (hp)
+                {
+                    const int tc = tcount[s] + (int)__dp4a(hp, 0x01010101u, 0u);
+                    tcount[s] = tc;
+                    mass[s] = mass0[s] + (double)tc;
+                    hpack[s] = 0;
+                }
             }
-            __syncwarp();
-            for (int s = lane; s < S; s += 32) { mass[s] += (double)hist[s]; hist[s] = 0; }
+        }
+        else
+        {
+            if (valid && warp == 0) atomicAdd(&tcount[c], 1);
+            __syncthreads();
+            for (int s = tid; s < S; s += blockDim.x) mass[s] = mass0[s] + (double)tcount[s];
         }
         __syncthreads();
         if (blk_next == 0) ++sweep;
@@ -480,7 +597,7 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
         atomicAdd(&counters[0], rounds);
         atomicAdd(&counters[1], passes);
     }
-    if (warp != 0) return;
+    if (tid >= 32) return;
     // normalise the masses; fold the averaged counts into the models (lines 217-243)
     double z = 0;
     for (int s = 0; s < S; ++s) z += mass[s];
@@ -521,6 +638,30 @@ __global__ void k_init_models(double* sub, int n_slots, double e)
 
 }  // namespace
 
+// dynamic shared memory of k_gibbs<NG> (the carve-up at the top of the kernel)
+static size_t gibbs_smem_bytes(int ng, int smem_S)
+{
+    return sizeof(double) * ((size_t)3 * ng * smem_S * 32 + 2 * (size_t)smem_S + (size_t)5 * ng * GIBBS_NW * 32 + 2) +
+           sizeof(int) * ((size_t)smem_S * 10);
+}
+
+static int g_gibbs_blocks = 0;  // rambl_set_gibbs_blocks
+
+template <int NG>
+static void launch_gibbs(const StepLaunch& L, int smem_S, cudaStream_t st)
+{
+    const size_t smem = gibbs_smem_bytes(NG, smem_S);
+    static size_t configured = 0;
+    if (smem > configured)
+    {
+        RAMBL_CUDA(cudaFuncSetAttribute(k_gibbs<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_gibbs<NG><<<L.n_groups, 128 * NG, smem, st>>>(L.groups, L.iarena, L.darena, L.weights, L.uniforms, L.counters, smem_S);
+}
+
+void set_gibbs_blocks(int blocks) { g_gibbs_blocks = blocks; }
+
 void launch_level_step(const StepLaunch& L, cudaStream_t st, int* launches)
 {
     if (L.n_groups == 0) return;
@@ -544,14 +685,15 @@ void launch_level_step(const StepLaunch& L, cudaStream_t st, int* launches)
     {
         if (L.gibbs_begin) RAMBL_CUDA(cudaEventRecord(L.gibbs_begin, st));
         const int smem_S = (L.max_S + 3) & ~3;
-        const size_t smem = sizeof(double) * ((size_t)smem_S * 97 + 4 * 32 + 2 * 3 * 4 * 32 + 2) + sizeof(int) * ((size_t)smem_S * 9 + 32);
-        static size_t configured = 0;
-        if (smem > configured)
-        {
-            RAMBL_CUDA(cudaFuncSetAttribute(k_gibbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
-        k_gibbs<<<L.n_groups, 128, smem, st>>>(L.groups, L.iarena, L.darena, L.weights, L.uniforms, L.counters, smem_S);
+        // 32-draw blocks per round: a few subgroups leave SMs idle, so their chains go wide (as far as the
+        // shared memory of one SM carries S strains); a batch of hundreds is faster as narrow CTAs, several
+        // per SM.  The chain -- and so every result -- is the same for any NG.
+        int ng = L.n_groups <= 148 ? 4 : (L.n_groups <= 296 ? 2 : 1);
+        if (g_gibbs_blocks > 0) ng = g_gibbs_blocks;
+        while (ng > 1 && gibbs_smem_bytes(ng, smem_S) > 227 * 1024) ng >>= 1;
+        if (ng == 4) launch_gibbs<4>(L, smem_S, st);
+        else if (ng == 2) launch_gibbs<2>(L, smem_S, st);
+        else launch_gibbs<1>(L, smem_S, st);
         if (L.gibbs_end) RAMBL_CUDA(cudaEventRecord(L.gibbs_end, st));
         ++*launches;
     }

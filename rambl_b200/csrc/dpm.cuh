@@ -64,6 +64,7 @@ struct StepLaunch
     cudaEvent_t gibbs_begin = nullptr, gibbs_end = nullptr;  // optional: bracket the k_gibbs launch
 };
 
+void set_gibbs_blocks(int blocks);  // 0 = automatic, else 1, 2 or 4 blocks of 32 draws per round
 void launch_level_step(const StepLaunch& L, cudaStream_t st, int* launches);
 void launch_inherit(const InheritOp* d_ops, int n_ops, long long max_stride, cudaStream_t st, int* launches);
 void launch_init_models(double* sub, int n_slots, double e, cudaStream_t st, int* launches);

@@ -196,6 +196,24 @@ def test_batch_equals_one_by_one():
         assert together.output_edge(i) == alone.output_edge(0)
 
 
+def test_gibbs_block_count_does_not_change_the_chain():
+    """The Gibbs kernel speculates over 1, 2 or 4 blocks of 32 draws per round; each setting must settle on
+    the same sequential chain, so every output is identical text (and identical to the oracle's strains)."""
+    sgs = [synth.make_subgroup(**fuzz_spec(s)) for s in (1, 2, 6, 9, 15)]
+    sgs.append(synth.make_subgroup(n_reads=800, read_len=100, n_strains=4, seed=31, window=(300, 520)))
+    texts = {}
+    try:
+        for blocks in (1, 2, 4):
+            assert api.lib().rambl_set_gibbs_blocks(blocks) == api.RAMBL_OK
+            b = _solve(sgs)
+            texts[blocks] = [(b.status(i), b.strains_text(i)) for i in range(len(sgs))]
+    finally:
+        api.lib().rambl_set_gibbs_blocks(0)
+    assert api.lib().rambl_set_gibbs_blocks(3) == api.RAMBL_ERR_INVALID
+    assert texts[1] == texts[2] == texts[4]
+    assert any(st == api.RAMBL_OK for st, _ in texts[1])
+
+
 def test_paired_reads_and_copies():
     sg = synth.make_subgroup(n_reads=300, read_len=30, n_strains=2, seed=4, window=(500, 580), sub_err=0.002,
                              paired=True, divergence=(0.03, 0.06))

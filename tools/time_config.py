@@ -14,6 +14,8 @@ def main():
     from rambl_b200 import api, synth
     idx = int(sys.argv[1]); scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    if os.environ.get("RAMBL_GIBBS_NG"):
+        assert api.lib().rambl_set_gibbs_blocks(int(os.environ["RAMBL_GIBBS_NG"])) == 0
     t = time.time()
     if idx == 2:  # 500 subgroups x 5k reads: generate on all host cores
         import multiprocessing as mp
