@@ -57,9 +57,10 @@ void rambl_free(void* p); /* for every char* this library returns */
 /* Device and pinned-host buffers are cached between calls (cudaMalloc/cudaFree cost up to a second per
  * strain search); this returns the cached blocks to the driver. */
 void rambl_release_cached_memory(void);
-/* The Gibbs-sweep kernel takes 1, 2 or 4 blocks of 32 draws per round; 0 (the default) lets the library
- * choose by batch size and strain count.  Every setting computes the same chain -- this is a measurement
- * and test hook, not a results knob.  Returns RAMBL_ERR_INVALID for any other value. */
+/* The Gibbs-sweep kernels take 1, 2, 4 or 8 blocks of 32 draws per round; 0 (the default) lets the library
+ * choose by batch size and strain count.  -1, -2, -4 pin the block count AND the four-warps-per-block kernel
+ * that otherwise serves only levels of more than 64 strains.  Every setting computes the same chain -- this
+ * is a measurement and test hook, not a results knob.  Returns RAMBL_ERR_INVALID for any other value. */
 int rambl_set_gibbs_blocks(int32_t blocks);
 
 /* ---- MultipleSequenceAlignmentSP<Index2D,SimpleScoreModel,vector,string,char>::align

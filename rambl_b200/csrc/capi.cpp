@@ -214,7 +214,8 @@ void rambl_release_cached_memory(void) { release_cached_memory(); }
 
 int rambl_set_gibbs_blocks(int32_t blocks)
 {
-    if (blocks != 0 && blocks != 1 && blocks != 2 && blocks != 4) return RAMBL_ERR_INVALID;
+    const int a = blocks < 0 ? -blocks : blocks;
+    if (a != 0 && a != 1 && a != 2 && a != 4 && !(blocks == 8)) return RAMBL_ERR_INVALID;
     set_gibbs_blocks(blocks);
     return RAMBL_OK;
 }

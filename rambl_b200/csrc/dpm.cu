@@ -619,6 +619,337 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
     }
 }
 
+// The same chain with ONE warp per 32-draw block and up to eight blocks (256 draws) per round, for levels of
+// at most 64 candidate strains (the reference prunes to about 80 and usually holds 10-50).  A warp keeps its
+// block to itself -- no partial sums to exchange, no barriers inside a block -- and spends about a third of
+// the instructions per draw of k_gibbs, which is what bounds a round once several warps share a scheduler:
+//   * cumulative weights are not stored: phase A forms the four chunk totals (four independent fma chains),
+//     phase B re-runs the one chunk that holds u * total and keeps the two cumulative weights around the pick
+//     in registers (the check needs nothing else), so shared memory holds the weights only;
+//   * every pick of the round is published as a per-strain count (byte b of hpack = block b) and, for the
+//     block's own lanes, a per-strain lane mask; draw j of block b is corrected by
+//         corr_j(s) = sum_{s' <= s} (picks of s' in blocks < b  +  picks of s' on lanes < j of block b) * w_j[s']
+//     summed in strain order over the strains with a non-zero count (a short per-warp list, rebuilt every
+//     pass by ballot, walked four entries at a time so that the shared-memory loads overlap);
+//   * a pick that fails its check is re-derived by its warp, candidate strain s on lane s % 32, with the same
+//     sums in the same order, so check and re-derivation cannot disagree.
+// cum(s) = off[chunk of s] + (fma chain from the start of that chunk), as in k_gibbs.
+constexpr int GIBBS_LIST = 72;  // 64 strains + padding
+
+template <int NB>
+__global__ void __launch_bounds__(32 * NB, 1)
+k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, double* __restrict__ Dar,
+          double* __restrict__ W, const double* __restrict__ U, unsigned long long* counters, int smem_S)
+{
+    const StepGroup g = groups[blockIdx.x];
+    if (g.mode != MODE_GIBBS && g.mode != MODE_ASSIGN) return;
+    extern __shared__ __align__(128) double gibbs_smem[];  // sized for the largest S of the launch (smem_S <= 64)
+    double* wbuf = gibbs_smem;                       // [2][block][strain][lane] weights of a round (bulk-copied)
+    double* mass = wbuf + 2 * NB * smem_S * 32;      // [smem_S] masses at the start of the round
+    double* mass0 = mass + smem_S;                   // [smem_S] masses at the start of the launch
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(mass0 + smem_S);  // [2]
+    unsigned long long* hpack = bars + 2;            // [smem_S] picks per strain in this round, byte b = block b
+    uint2* lists = reinterpret_cast<uint2*>(hpack + smem_S);        // [block][GIBBS_LIST] the strains that count for block b
+    unsigned* pmask = reinterpret_cast<unsigned*>(lists + NB * GIBBS_LIST);  // [block][smem_S] lanes of block b that picked s
+    int* tcount = reinterpret_cast<int*>(pmask + NB * smem_S);      // [smem_S] picks per strain since the launch began
+    int* cnt = tcount + smem_S;                      // [smem_S][8]
+    const int tid = threadIdx.x, lane = tid & 31, b = tid >> 5;
+    const int S = g.S, D = g.D;
+    const unsigned full = 0xffffffffu;
+    const double* wt = group_weights(W, g);
+    const int* code = group_codes(W, g);
+    const int Dp = padded_draws(D);
+    for (int k = tid; k < S * 8; k += blockDim.x) cnt[k] = 0;
+    for (int k = tid; k < NB * smem_S; k += blockDim.x) pmask[k] = 0;
+    for (int s = tid; s < S; s += blockDim.x)
+    {
+        const double a = Dar[g.ab_off + s];
+        mass[s] = a; mass0[s] = a; hpack[s] = 0; tcount[s] = 0;
+    }
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int tiles = Dp / 32;                       // tiles of 32 draws per sweep
+    const int per_sweep = (tiles + NB - 1) / NB;     // rounds per sweep (the last one may be short of blocks)
+    const long long n_rounds = (S >= 2) ? (long long)g.nsweeps * per_sweep : 0;
+    unsigned long long rounds = 0, passes = 0;
+    auto stage = [&](long long r, int blk) {
+        if (tid == 0)
+        {
+            const int bf = (int)(r & 1);
+            const unsigned bytes = (unsigned)min(NB, tiles - blk * NB) * (unsigned)S * 256u;
+            mbar_expect_tx(&bars[bf], bytes);
+            bulk_g2s(wbuf + (size_t)bf * NB * smem_S * 32, wt + (long long)blk * NB * S * 32, bytes, &bars[bf]);
+        }
+    };
+    if (n_rounds > 0) stage(0, 0);
+    int sweep = 0, blk = 0;
+    const int Cs = (S + GIBBS_NW - 1) / GIBBS_NW;    // strains per chunk
+    const unsigned long long below = (b == 0) ? 0ull : (~0ull >> (64 - 8 * b));  // the bytes of hpack that precede this block
+    const unsigned below_lo = (unsigned)below, below_hi = (unsigned)(below >> 32);
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned char* hbytes = reinterpret_cast<unsigned char*>(hpack);
+    unsigned* pm = pmask + b * smem_S;
+    uint2* list = lists + b * GIBBS_LIST;
+    double u_next = 0.0;
+    int cd_next = 0;
+    if (n_rounds > 0)
+    {
+        const int d0 = b * 32 + lane;
+        if (b < tiles && d0 < D)
+        {
+            u_next = U[d0];
+            if (g.mode == MODE_GIBBS) cd_next = code[d0];
+        }
+    }
+    for (long long r = 0; r < n_rounds; ++r)
+    {
+        const bool active = b < tiles - blk * NB;    // a short last round leaves the high blocks idle
+        const int d = (blk * NB + b) * 32 + lane;
+        const bool valid = active && d < D;
+        const double u = u_next;
+        const int cd = cd_next;
+        const int blk_next = (blk + 1 == per_sweep) ? 0 : blk + 1;
+        if (r + 1 < n_rounds)
+        {
+            stage(r + 1, blk_next);  // overlaps this round's arithmetic
+            const int dn = (blk_next * NB + b) * 32 + lane;
+            const int sweep_n = sweep + (blk_next == 0 ? 1 : 0);
+            const bool vn = b < tiles - blk_next * NB && dn < D;
+            u_next = vn ? U[(long long)sweep_n * D + dn] : 0.0;
+            cd_next = (vn && g.mode == MODE_GIBBS) ? code[dn] : 0;
+        }
+        mbar_wait(&bars[r & 1], (unsigned)((r >> 1) & 1));
+        const double* wl = wbuf + ((size_t)(r & 1) * NB * smem_S + (size_t)b * S) * 32 + lane;
+        double off[GIBBS_NW + 1];
+        off[0] = 0;
+        double base_tot = 0, b_prev = 0, b_here = 0;  // cum(c-1) and cum(c) without corrections
+        int c = -1;
+        if (active)
+        {
+            // ---- phase A: the four chunk totals, four independent chains in strain order
+            double ch[GIBBS_NW];
+#pragma unroll
+            for (int q = 0; q < GIBBS_NW; ++q) ch[q] = 0;
+            for (int k = 0; k < Cs; ++k)
+            {
+#pragma unroll
+                for (int q = 0; q < GIBBS_NW; ++q)
+                {
+                    const int s = q * Cs + k;
+                    if (s < S) ch[q] = fma(mass[s], wl[s * 32], ch[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < GIBBS_NW; ++q) off[q + 1] = off[q] + ch[q];
+            base_tot = off[GIBBS_NW];
+            // ---- phase B: lower_bound of u*total over the cumulative weights of strains 0..S-2 (S-1 if none
+            // reaches it): the chunk first, then the chain of that chunk once more with the comparison riding along
+            const double thr = u * base_tot;
+            int q = 0;
+#pragma unroll
+            for (int k = 1; k < GIBBS_NW; ++k) q += (off[k] < thr) ? 1 : 0;
+            double oq = 0;
+#pragma unroll
+            for (int k = 1; k < GIBBS_NW; ++k) oq = (q == k) ? off[k] : oq;
+            const int lo = q * Cs, end = min(lo + Cs, S - 1);  // candidates lo..end-1
+            double run = 0;
+            bool found = false;
+            int cn = lo;
+            b_prev = oq;  // cum(lo-1) is the same number as off[q]
+            for (int k = 0; k < Cs; ++k)
+            {
+                const int s = lo + k;
+                const bool in = s < end;
+                const int sc = in ? s : 0;
+                run = fma(mass[sc], wl[sc * 32], run);
+                const double v = oq + run;
+                const bool take = in && !found;
+                const bool under = v < thr;
+                if (take && under) { b_prev = v; ++cn; }
+                if (take && !under) { b_here = v; found = true; }
+            }
+            c = valid ? min(cn, S - 1) : -1;
+        }
+        ++passes;
+        // ---- settle: check every pick against the picks of the earlier draws until nothing moves
+        int settle_passes = 0;
+        int c_pub = -1;  // what this lane has published
+        for (;;)
+        {
+            if (active)
+            {
+                if (c_pub >= 0) { hbytes[c_pub * 8 + b] = 0; pm[c_pub] = 0; }
+                __syncwarp();
+                const unsigned same = __match_any_sync(full, c);
+                if (c >= 0 && lane == __ffs(same) - 1)
+                {
+                    hbytes[c * 8 + b] = (unsigned char)__popc(same);
+                    pm[c] = same;
+                }
+                c_pub = c;
+            }
+            __syncthreads();
+            bool moved = false;
+            if (active)
+            {
+                // the strains that count for this block (picked in an earlier block or on a lane of this one), in
+                // strain order, as a list of (strain, picks in earlier blocks, lanes of this block): lane i looks at
+                // strains i and i+32; the list is padded to a multiple of four with entries that add nothing
+                int n_list;
+                {
+                    const bool in0 = lane < S, in1 = lane + 32 < S;
+                    const unsigned long long hp0 = in0 ? hpack[lane] : 0ull, hp1 = in1 ? hpack[lane + 32] : 0ull;
+                    const unsigned mm0 = in0 ? pm[lane] : 0u, mm1 = in1 ? pm[lane + 32] : 0u;
+                    const unsigned hs0 = __dp4a((unsigned)hp0 & below_lo, 0x01010101u, __dp4a((unsigned)(hp0 >> 32) & below_hi, 0x01010101u, 0u));
+                    const unsigned hs1 = __dp4a((unsigned)hp1 & below_lo, 0x01010101u, __dp4a((unsigned)(hp1 >> 32) & below_hi, 0x01010101u, 0u));
+                    const unsigned bal0 = __ballot_sync(full, (hs0 | mm0) != 0), bal1 = __ballot_sync(full, (hs1 | mm1) != 0);
+                    const int n0 = __popc(bal0);
+                    n_list = n0 + __popc(bal1);
+                    if (hs0 | mm0) list[__popc(bal0 & lt)] = make_uint2((unsigned)lane | (hs0 << 8), mm0);
+                    if (hs1 | mm1) list[n0 + __popc(bal1 & lt)] = make_uint2((unsigned)(lane + 32) | (hs1 << 8), mm1);
+                    if (lane < 4) list[n_list + lane] = make_uint2(0u, 0u);
+                    __syncwarp();
+                }
+                double p_prev = 0, p_here = 0, p_tot = 0;
+                for (int i = 0; i < n_list; i += 4)
+                {
+                    uint2 e[4];
+                    double w4[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) e[k] = list[i + k];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) w4[k] = wl[(e[k].x & 0xffu) * 32];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const int s = (int)(e[k].x & 0xffu);
+                        const double kd = (double)((int)(e[k].x >> 8) + __popc(e[k].y & lt));
+                        p_tot = fma(w4[k], kd, p_tot);
+                        p_here = fma(w4[k], (s <= c) ? kd : 0.0, p_here);
+                        p_prev = fma(w4[k], (s < c) ? kd : 0.0, p_prev);
+                    }
+                }
+                const double thr = u * (base_tot + p_tot);
+                bool ok = true;
+                if (valid)
+                {
+                    const bool lo_ok = (c == 0) || (b_prev + p_prev < thr);
+                    const bool hi_ok = (c == S - 1) || !(b_here + p_here < thr);
+                    ok = lo_ok && hi_ok;
+                }
+                unsigned failed = __ballot_sync(full, !ok);
+                while (failed)
+                {
+                    const int f = __ffs(failed) - 1;
+                    failed &= failed - 1;
+                    const double thr_f = __shfl_sync(full, thr, f);
+                    double off_f[GIBBS_NW];
+#pragma unroll
+                    for (int q = 1; q < GIBBS_NW; ++q) off_f[q] = __shfl_sync(full, off[q], f);
+                    const double* wf = wl - lane + f;  // the weights of draw f
+                    const unsigned lt_f = (1u << f) - 1u;
+                    int cn = S - 1;
+                    double carry = 0, bp_new = 0, bh_new = 0;
+                    bool hit_any = false;
+                    for (int s0 = 0; s0 < S - 1 && !hit_any; s0 += 32)
+                    {
+                        const int s = s0 + lane;
+                        const int q = (s >= Cs ? 1 : 0) + (s >= 2 * Cs ? 1 : 0) + (s >= 3 * Cs ? 1 : 0);
+                        const int lo = q * Cs;
+                        double acc = 0;  // chain of the chunk of s, from its start up to s
+                        const int t_end = min(S, s0 + 32);
+                        for (int t = 0; t < t_end; ++t)
+                        {
+                            const double m = mass[t], w = wf[t * 32];
+                            if (t >= lo && t <= s) acc = fma(m, w, acc);
+                        }
+                        double o = 0;
+#pragma unroll
+                        for (int k = 1; k < GIBBS_NW; ++k) o = (q == k) ? off_f[k] : o;
+                        const double base = o + acc;
+                        double p = 0;
+                        for (int i = 0; i < n_list; ++i)
+                        {
+                            const uint2 e = list[i];
+                            const int t = (int)(e.x & 0xffu);
+                            const int k = (int)(e.x >> 8) + __popc(e.y & lt_f);
+                            p = fma(wf[t * 32], (t <= s) ? (double)k : 0.0, p);
+                        }
+                        // strain S-1 is the fallback of the lower bound: it and the padding lanes count as "reached"
+                        const bool reached = (s >= S - 1) || !(base + p < thr_f);
+                        const unsigned hit = __ballot_sync(full, reached);
+                        if (hit)
+                        {
+                            const int th = __ffs(hit) - 1;
+                            cn = min(s0 + th, S - 1);
+                            bh_new = __shfl_sync(full, base, th);
+                            const double below_hit = __shfl_sync(full, base, max(th - 1, 0));
+                            bp_new = th > 0 ? below_hit : carry;
+                            hit_any = true;
+                        }
+                        else carry = __shfl_sync(full, base, 31);
+                    }
+                    if (!hit_any) bp_new = carry;  // only when S-1 is a multiple of 32: the fallback strain, cum(S-2) below it
+                    if (lane == f)
+                    {
+                        moved = moved || (cn != c);
+                        c = cn; b_prev = bp_new; b_here = bh_new;
+                    }
+                }
+            }
+            ++passes;
+            // draw 32b+j is final after 32b+j+1 passes, so 32*NB+1 passes always suffice -- the cap only guards
+            // the device against a launch that does not terminate
+            const int any_moved = __syncthreads_or(moved ? 1 : 0);  // also orders this pass before the next publication
+            if (!any_moved || ++settle_passes > 32 * NB + 8) break;
+        }
+        ++rounds;
+        // ---- commit: letter statistics, then the masses of the next round from the exact pick counts
+        if (valid && g.mode == MODE_GIBBS) atomicAdd(&cnt[c * 8 + cd], 1);
+        if (active && c_pub >= 0) pm[c_pub] = 0;
+        for (int s = tid; s < S; s += blockDim.x)
+        {
+            const unsigned long long hp = hpack[s];
+            if (hp)
+            {
+                const int tc = tcount[s] + (int)__dp4a((unsigned)hp, 0x01010101u, __dp4a((unsigned)(hp >> 32), 0x01010101u, 0u));
+                tcount[s] = tc;
+                mass[s] = mass0[s] + (double)tc;
+                hpack[s] = 0;
+            }
+        }
+        __syncthreads();
+        if (blk_next == 0) ++sweep;
+        blk = blk_next;
+    }
+    if (tid == 0 && counters)
+    {
+        atomicAdd(&counters[0], rounds);
+        atomicAdd(&counters[1], passes);
+    }
+    if (tid >= 32) return;
+    // normalise the masses; fold the averaged counts into the models (lines 217-243)
+    double z = 0;
+    for (int s = 0; s < S; ++s) z += mass[s];
+    for (int s = lane; s < S; s += 32)
+    {
+        double v = mass[s] / z;
+        if (g.mode == MODE_GIBBS) v *= (double)g.read_size;
+        Dar[g.ab_off + s] = v;
+        if (g.mode == MODE_GIBBS && I[g.lab_off + S + s] == 1)
+        {
+            const int la = letter_code(g.label_chars[I[g.lab_off + s]]);
+            if (la < 6)
+            {
+                double* sub = g.sub + (long long)I[g.slot_off + s] * 36 + la * 6;
+                for (int bb = 0; bb < 6; ++bb)
+                    if (cnt[s * 8 + bb]) sub[bb] += (double)cnt[s * 8 + bb] / (double)g.nsweeps;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_inherit(const InheritOp* __restrict__ ops)
 {
     const InheritOp op = ops[blockIdx.y];
@@ -660,6 +991,25 @@ static void launch_gibbs(const StepLaunch& L, int smem_S, cudaStream_t st)
     k_gibbs<NG><<<L.n_groups, 128 * NG, smem, st>>>(L.groups, L.iarena, L.darena, L.weights, L.uniforms, L.counters, smem_S);
 }
 
+// dynamic shared memory of k_gibbs_w<NB>
+static size_t gibbs_w_smem_bytes(int nb, int smem_S)
+{
+    return 8 * ((size_t)64 * nb * smem_S + 3 * (size_t)smem_S + 2 + (size_t)nb * GIBBS_LIST) + 4 * ((size_t)nb * smem_S + 9 * (size_t)smem_S);
+}
+
+template <int NB>
+static void launch_gibbs_w(const StepLaunch& L, int smem_S, cudaStream_t st)
+{
+    const size_t smem = gibbs_w_smem_bytes(NB, smem_S);
+    static size_t configured = 0;
+    if (smem > configured)
+    {
+        RAMBL_CUDA(cudaFuncSetAttribute(k_gibbs_w<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_gibbs_w<NB><<<L.n_groups, 32 * NB, smem, st>>>(L.groups, L.iarena, L.darena, L.weights, L.uniforms, L.counters, smem_S);
+}
+
 void set_gibbs_blocks(int blocks) { g_gibbs_blocks = blocks; }
 
 void launch_level_step(const StepLaunch& L, cudaStream_t st, int* launches)
@@ -686,14 +1036,29 @@ void launch_level_step(const StepLaunch& L, cudaStream_t st, int* launches)
         if (L.gibbs_begin) RAMBL_CUDA(cudaEventRecord(L.gibbs_begin, st));
         const int smem_S = (L.max_S + 3) & ~3;
         // 32-draw blocks per round: a few subgroups leave SMs idle, so their chains go wide (as far as the
-        // shared memory of one SM carries S strains); a batch of hundreds is faster as narrow CTAs, several
-        // per SM.  The chain -- and so every result -- is the same for any NG.
-        int ng = L.n_groups <= 148 ? 4 : (L.n_groups <= 296 ? 2 : 1);
-        if (g_gibbs_blocks > 0) ng = g_gibbs_blocks;
-        while (ng > 1 && gibbs_smem_bytes(ng, smem_S) > 227 * 1024) ng >>= 1;
-        if (ng == 4) launch_gibbs<4>(L, smem_S, st);
-        else if (ng == 2) launch_gibbs<2>(L, smem_S, st);
-        else launch_gibbs<1>(L, smem_S, st);
+        // shared memory of one SM carries S strains); a batch of hundreds fills the SMs with narrow CTAs,
+        // several per SM.  Levels of at most 64 strains take the warp-per-block kernel, wider ones the
+        // four-warps-per-block kernel.  The chain -- and so every result -- is the same for any choice.
+        int nb = L.n_groups <= 148 ? 8 : (L.n_groups <= 296 ? 4 : 2);
+        bool warp_per_block = L.max_S <= 64;
+        if (g_gibbs_blocks > 0) nb = g_gibbs_blocks;
+        if (g_gibbs_blocks < 0) { nb = -g_gibbs_blocks; warp_per_block = false; }
+        if (warp_per_block)
+        {
+            while (nb > 1 && gibbs_w_smem_bytes(nb, smem_S) > 227 * 1024) nb >>= 1;
+            if (nb == 8) launch_gibbs_w<8>(L, smem_S, st);
+            else if (nb == 4) launch_gibbs_w<4>(L, smem_S, st);
+            else if (nb == 2) launch_gibbs_w<2>(L, smem_S, st);
+            else launch_gibbs_w<1>(L, smem_S, st);
+        }
+        else
+        {
+            nb = nb > 4 ? 4 : nb;
+            while (nb > 1 && gibbs_smem_bytes(nb, smem_S) > 227 * 1024) nb >>= 1;
+            if (nb == 4) launch_gibbs<4>(L, smem_S, st);
+            else if (nb == 2) launch_gibbs<2>(L, smem_S, st);
+            else launch_gibbs<1>(L, smem_S, st);
+        }
         if (L.gibbs_end) RAMBL_CUDA(cudaEventRecord(L.gibbs_end, st));
         ++*launches;
     }

@@ -197,20 +197,22 @@ def test_batch_equals_one_by_one():
 
 
 def test_gibbs_block_count_does_not_change_the_chain():
-    """The Gibbs kernel speculates over 1, 2 or 4 blocks of 32 draws per round; each setting must settle on
-    the same sequential chain, so every output is identical text (and identical to the oracle's strains)."""
+    """The Gibbs kernels speculate over 1 to 8 blocks of 32 draws per round (positive: kernel chosen by strain
+    count, negative: the four-warps-per-block kernel); each setting must settle on the same sequential chain,
+    so every output is identical text."""
     sgs = [synth.make_subgroup(**fuzz_spec(s)) for s in (1, 2, 6, 9, 15)]
     sgs.append(synth.make_subgroup(n_reads=800, read_len=100, n_strains=4, seed=31, window=(300, 520)))
     texts = {}
     try:
-        for blocks in (1, 2, 4):
+        for blocks in (1, 2, 4, 8, -1, -2, -4):
             assert api.lib().rambl_set_gibbs_blocks(blocks) == api.RAMBL_OK
             b = _solve(sgs)
             texts[blocks] = [(b.status(i), b.strains_text(i)) for i in range(len(sgs))]
     finally:
         api.lib().rambl_set_gibbs_blocks(0)
     assert api.lib().rambl_set_gibbs_blocks(3) == api.RAMBL_ERR_INVALID
-    assert texts[1] == texts[2] == texts[4]
+    for blocks in texts:
+        assert texts[blocks] == texts[1], blocks
     assert any(st == api.RAMBL_OK for st, _ in texts[1])
 
 
