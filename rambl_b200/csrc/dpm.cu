@@ -731,13 +731,30 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
             double ch[GIBBS_NW];
 #pragma unroll
             for (int q = 0; q < GIBBS_NW; ++q) ch[q] = 0;
-            for (int k = 0; k < Cs; ++k)
+            const int n_last = S - (GIBBS_NW - 1) * Cs;  // strains in the last chunk; the others are full when this is >= 0
+            if (n_last >= 0)
             {
-#pragma unroll
-                for (int q = 0; q < GIBBS_NW; ++q)
+                const double* m1 = mass + Cs; const double* m2 = m1 + Cs; const double* m3 = m2 + Cs;
+                const double* w1 = wl + Cs * 32; const double* w2 = w1 + Cs * 32; const double* w3 = w2 + Cs * 32;
+#pragma unroll 2
+                for (int k = 0; k < Cs; ++k)
                 {
-                    const int s = q * Cs + k;
-                    if (s < S) ch[q] = fma(mass[s], wl[s * 32], ch[q]);
+                    ch[0] = fma(mass[k], wl[k * 32], ch[0]);
+                    ch[1] = fma(m1[k], w1[k * 32], ch[1]);
+                    ch[2] = fma(m2[k], w2[k * 32], ch[2]);
+                    if (k < n_last) ch[3] = fma(m3[k], w3[k * 32], ch[3]);
+                }
+            }
+            else
+            {
+                for (int k = 0; k < Cs; ++k)
+                {
+#pragma unroll
+                    for (int q = 0; q < GIBBS_NW; ++q)
+                    {
+                        const int s = q * Cs + k;
+                        if (s < S) ch[q] = fma(mass[s], wl[s * 32], ch[q]);
+                    }
                 }
             }
 #pragma unroll
@@ -811,7 +828,13 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
                     if (lane < 4) list[n_list + lane] = make_uint2(0u, 0u);
                     __syncwarp();
                 }
-                double p_prev = 0, p_here = 0, p_tot = 0;
+                // corr(S-1) and corr(c-1) as chains over the list; corr(c) is the second chain taken one term further
+                // -- the term of strain c itself, which this lane looks up directly (zero if c is not on the list)
+                const int cc = max(c, 0);
+                const unsigned long long hpc = hpack[cc];
+                const unsigned mmc = pm[cc];
+                const double w_c = wl[cc * 32];
+                double p_prev = 0, p_tot = 0;
                 for (int i = 0; i < n_list; i += 4)
                 {
                     uint2 e[4];
@@ -826,10 +849,12 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
                         const int s = (int)(e[k].x & 0xffu);
                         const double kd = (double)((int)(e[k].x >> 8) + __popc(e[k].y & lt));
                         p_tot = fma(w4[k], kd, p_tot);
-                        p_here = fma(w4[k], (s <= c) ? kd : 0.0, p_here);
                         p_prev = fma(w4[k], (s < c) ? kd : 0.0, p_prev);
                     }
                 }
+                const int k_c = (int)__dp4a((unsigned)hpc & below_lo, 0x01010101u, __dp4a((unsigned)(hpc >> 32) & below_hi, 0x01010101u, 0u)) +
+                                __popc(mmc & lt);
+                const double p_here = fma(w_c, (double)k_c, p_prev);
                 const double thr = u * (base_tot + p_tot);
                 bool ok = true;
                 if (valid)
@@ -1039,13 +1064,17 @@ void launch_level_step(const StepLaunch& L, cudaStream_t st, int* launches)
         // shared memory of one SM carries S strains); a batch of hundreds fills the SMs with narrow CTAs,
         // several per SM.  Levels of at most 64 strains take the warp-per-block kernel, wider ones the
         // four-warps-per-block kernel.  The chain -- and so every result -- is the same for any choice.
-        int nb = L.n_groups <= 148 ? 8 : (L.n_groups <= 296 ? 4 : 2);
+        int nb = 8;
         bool warp_per_block = L.max_S <= 64;
         if (g_gibbs_blocks > 0) nb = g_gibbs_blocks;
         if (g_gibbs_blocks < 0) { nb = -g_gibbs_blocks; warp_per_block = false; }
         if (warp_per_block)
         {
-            while (nb > 1 && gibbs_w_smem_bytes(nb, smem_S) > 227 * 1024) nb >>= 1;
+            // the widest CTA that still lets every subgroup of the launch be resident at once
+            const size_t sm_bytes = 227 * 1024;
+            while (nb > 1 && (gibbs_w_smem_bytes(nb, smem_S) > sm_bytes ||
+                              (g_gibbs_blocks == 0 && 148 * (sm_bytes / gibbs_w_smem_bytes(nb, smem_S)) < (size_t)L.n_groups)))
+                nb >>= 1;
             if (nb == 8) launch_gibbs_w<8>(L, smem_S, st);
             else if (nb == 4) launch_gibbs_w<4>(L, smem_S, st);
             else if (nb == 2) launch_gibbs_w<2>(L, smem_S, st);
@@ -1054,6 +1083,7 @@ void launch_level_step(const StepLaunch& L, cudaStream_t st, int* launches)
         else
         {
             nb = nb > 4 ? 4 : nb;
+            if (g_gibbs_blocks == 0 && L.n_groups > 148) nb = 1;
             while (nb > 1 && gibbs_smem_bytes(nb, smem_S) > 227 * 1024) nb >>= 1;
             if (nb == 4) launch_gibbs<4>(L, smem_S, st);
             else if (nb == 2) launch_gibbs<2>(L, smem_S, st);
