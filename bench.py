@@ -337,7 +337,7 @@ def main():
     peak, peak_src = measured_peak_gbs()
     gibbs_s = agg.get("gibbs_kernel_ms", 0.0) / 1000.0
     achieved = (agg.get("gibbs_alg_bytes", 0) / 1e9) / gibbs_s if gibbs_s > 0 else 0.0
-    roofline = {"kernel": "k_gibbs (speculative block Gibbs sweeps)", "bound": "hbm", "achieved": achieved, "peak": peak,
+    roofline = {"kernel": "k_gibbs_w (speculative block Gibbs sweeps, one warp per 32-draw block, up to 8 blocks per round)", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": GIBBS_DRAM_BYTES_PER_LAUNCH,
                 "algorithmic_bytes_per_launch": (agg.get("gibbs_alg_bytes", 0) / agg["gibbs_launches"]) if agg.get("gibbs_launches") else None,
                 "avg_launch_ms": (agg.get("gibbs_kernel_ms", 0.0) / agg["gibbs_launches"]) if agg.get("gibbs_launches") else None,

@@ -645,14 +645,13 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
     if (g.mode != MODE_GIBBS && g.mode != MODE_ASSIGN) return;
     extern __shared__ __align__(128) double gibbs_smem[];  // sized for the largest S of the launch (smem_S <= 64)
     double* wbuf = gibbs_smem;                       // [2][block][strain][lane] weights of a round (bulk-copied)
-    double* mass = wbuf + 2 * NB * smem_S * 32;      // [smem_S] masses at the start of the round
-    double* mass0 = mass + smem_S;                   // [smem_S] masses at the start of the launch
+    double* masses = wbuf + 2 * NB * smem_S * 32;    // [block][smem_S] masses at the start of the round, one copy per warp
+    double* mass0 = masses + NB * smem_S;            // [smem_S] masses at the start of the launch
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(mass0 + smem_S);  // [2]
-    unsigned long long* hpack = bars + 2;            // [smem_S] picks per strain in this round, byte b = block b
-    uint2* lists = reinterpret_cast<uint2*>(hpack + smem_S);        // [block][GIBBS_LIST] the strains that count for block b
+    unsigned long long* hpacks = bars + 2;           // [2][smem_S] picks per strain in a round (by round parity), byte b = block b
+    uint2* lists = reinterpret_cast<uint2*>(hpacks + 2 * smem_S);   // [block][GIBBS_LIST] the strains that count for block b
     unsigned* pmask = reinterpret_cast<unsigned*>(lists + NB * GIBBS_LIST);  // [block][smem_S] lanes of block b that picked s
-    int* tcount = reinterpret_cast<int*>(pmask + NB * smem_S);      // [smem_S] picks per strain since the launch began
-    int* cnt = tcount + smem_S;                      // [smem_S][8]
+    int* cnt = reinterpret_cast<int*>(pmask + NB * smem_S);         // [smem_S][8]
     const int tid = threadIdx.x, lane = tid & 31, b = tid >> 5;
     const int S = g.S, D = g.D;
     const unsigned full = 0xffffffffu;
@@ -664,62 +663,80 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
     for (int s = tid; s < S; s += blockDim.x)
     {
         const double a = Dar[g.ab_off + s];
-        mass[s] = a; mass0[s] = a; hpack[s] = 0; tcount[s] = 0;
+        mass0[s] = a; hpacks[s] = 0; hpacks[smem_S + s] = 0;
+        for (int k = 0; k < NB; ++k) masses[k * smem_S + s] = a;
     }
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    // The chain is one stream of tiles: tile T = sweep * tiles + t holds draws 32t..32t+31 of that sweep, and round
+    // r takes tiles r*NB .. r*NB+NB-1 whatever sweep they fall in (the weights of tile t are the same in every
+    // sweep), so only the very last round can be short of blocks.
     const int tiles = Dp / 32;                       // tiles of 32 draws per sweep
-    const int per_sweep = (tiles + NB - 1) / NB;     // rounds per sweep (the last one may be short of blocks)
-    const long long n_rounds = (S >= 2) ? (long long)g.nsweeps * per_sweep : 0;
+    const int total_tiles = (S >= 2) ? g.nsweeps * tiles : 0;   // <= 5000 sweeps x 40000/32 tiles
+    const int n_rounds = (total_tiles + NB - 1) / NB;
     unsigned long long rounds = 0, passes = 0;
-    auto stage = [&](long long r, int blk) {
+    int stage_pos = 0;  // tile (within a sweep) the next staged round starts at; thread 0 only
+    // stage the weights of round r: its tiles are contiguous up to the end of a sweep, then wrap to tile 0
+    auto stage = [&](int r) {
         if (tid == 0)
         {
-            const int bf = (int)(r & 1);
-            const unsigned bytes = (unsigned)min(NB, tiles - blk * NB) * (unsigned)S * 256u;
-            mbar_expect_tx(&bars[bf], bytes);
-            bulk_g2s(wbuf + (size_t)bf * NB * smem_S * 32, wt + (long long)blk * NB * S * 32, bytes, &bars[bf]);
+            const int bf = r & 1;
+            int left = min(NB, total_tiles - r * NB);
+            mbar_expect_tx(&bars[bf], (unsigned)left * (unsigned)S * 256u);
+            double* dst = wbuf + (size_t)bf * NB * smem_S * 32;
+            while (left > 0)
+            {
+                const int seg = min(left, tiles - stage_pos);
+                bulk_g2s(dst, wt + (long long)stage_pos * S * 32, (unsigned)seg * (unsigned)S * 256u, &bars[bf]);
+                dst += (size_t)seg * S * 32;
+                left -= seg;
+                stage_pos += seg;
+                if (stage_pos == tiles) stage_pos = 0;
+            }
         }
     };
-    if (n_rounds > 0) stage(0, 0);
-    int sweep = 0, blk = 0;
+    if (n_rounds > 0) stage(0);
     const int Cs = (S + GIBBS_NW - 1) / GIBBS_NW;    // strains per chunk
     const unsigned long long below = (b == 0) ? 0ull : (~0ull >> (64 - 8 * b));  // the bytes of hpack that precede this block
     const unsigned below_lo = (unsigned)below, below_hi = (unsigned)(below >> 32);
     const unsigned lt = (1u << lane) - 1u;
-    unsigned char* hbytes = reinterpret_cast<unsigned char*>(hpack);
+    double* mass = masses + b * smem_S;  // this warp's copy: a round ends without a barrier (see the commit)
+    int tc0 = 0, tc1 = 0;                // picks of strains lane and lane+32 since the launch began
+    int c_last = -1;                     // this lane's final pick of the previous round
     unsigned* pm = pmask + b * smem_S;
     uint2* list = lists + b * GIBBS_LIST;
+    // this block's tile of the coming round: sweep and tile within the sweep; its uniform and read letter are
+    // fetched from global memory one round ahead
+    int sw_next = 0, t_next = b;
+    while (tiles > 0 && t_next >= tiles) { t_next -= tiles; ++sw_next; }
     double u_next = 0.0;
     int cd_next = 0;
-    if (n_rounds > 0)
+    if (b < total_tiles && t_next * 32 + lane < D)
     {
-        const int d0 = b * 32 + lane;
-        if (b < tiles && d0 < D)
-        {
-            u_next = U[d0];
-            if (g.mode == MODE_GIBBS) cd_next = code[d0];
-        }
+        u_next = U[(long long)sw_next * D + t_next * 32 + lane];
+        if (g.mode == MODE_GIBBS) cd_next = code[t_next * 32 + lane];
     }
-    for (long long r = 0; r < n_rounds; ++r)
+    for (int r = 0; r < n_rounds; ++r)
     {
-        const bool active = b < tiles - blk * NB;    // a short last round leaves the high blocks idle
-        const int d = (blk * NB + b) * 32 + lane;
+        const bool active = r * NB + b < total_tiles;  // only the last round can leave the high blocks idle
+        const int d = t_next * 32 + lane;
         const bool valid = active && d < D;
         const double u = u_next;
         const int cd = cd_next;
-        const int blk_next = (blk + 1 == per_sweep) ? 0 : blk + 1;
         if (r + 1 < n_rounds)
         {
-            stage(r + 1, blk_next);  // overlaps this round's arithmetic
-            const int dn = (blk_next * NB + b) * 32 + lane;
-            const int sweep_n = sweep + (blk_next == 0 ? 1 : 0);
-            const bool vn = b < tiles - blk_next * NB && dn < D;
-            u_next = vn ? U[(long long)sweep_n * D + dn] : 0.0;
+            stage(r + 1);  // overlaps this round's arithmetic
+            t_next += NB;
+            while (t_next >= tiles) { t_next -= tiles; ++sw_next; }
+            const int dn = t_next * 32 + lane;
+            const bool vn = (r + 1) * NB + b < total_tiles && dn < D;
+            u_next = vn ? U[(long long)sw_next * D + dn] : 0.0;
             cd_next = (vn && g.mode == MODE_GIBBS) ? code[dn] : 0;
         }
         mbar_wait(&bars[r & 1], (unsigned)((r >> 1) & 1));
+        unsigned long long* hpack = hpacks + (r & 1) * smem_S;
+        unsigned char* hbytes = reinterpret_cast<unsigned char*>(hpack);
         const double* wl = wbuf + ((size_t)(r & 1) * NB * smem_S + (size_t)b * S) * 32 + lane;
         double off[GIBBS_NW + 1];
         off[0] = 0;
@@ -727,22 +744,35 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
         int c = -1;
         if (active)
         {
-            // ---- phase A: the four chunk totals, four independent chains in strain order
-            double ch[GIBBS_NW];
+            // ---- phase A: the four chunk totals, four independent chains in strain order; each chain also leaves its
+            // value half-way through the chunk (after the first `half` strains), which lets phase B start there
+            double ch[GIBBS_NW], mid[GIBBS_NW];
 #pragma unroll
             for (int q = 0; q < GIBBS_NW; ++q) ch[q] = 0;
             const int n_last = S - (GIBBS_NW - 1) * Cs;  // strains in the last chunk; the others are full when this is >= 0
+            const int half = (Cs + 1) >> 1;
             if (n_last >= 0)
             {
-                const double* m1 = mass + Cs; const double* m2 = m1 + Cs; const double* m3 = m2 + Cs;
-                const double* w1 = wl + Cs * 32; const double* w2 = w1 + Cs * 32; const double* w3 = w2 + Cs * 32;
-#pragma unroll 2
-                for (int k = 0; k < Cs; ++k)
+                const double* mp = mass;
+                const double* wp = wl;
+                const int cs32 = Cs * 32;
+#pragma unroll 4
+                for (int k = 0; k < half; ++k, ++mp, wp += 32)
                 {
-                    ch[0] = fma(mass[k], wl[k * 32], ch[0]);
-                    ch[1] = fma(m1[k], w1[k * 32], ch[1]);
-                    ch[2] = fma(m2[k], w2[k * 32], ch[2]);
-                    if (k < n_last) ch[3] = fma(m3[k], w3[k * 32], ch[3]);
+                    ch[0] = fma(mp[0], wp[0], ch[0]);
+                    ch[1] = fma(mp[Cs], wp[cs32], ch[1]);
+                    ch[2] = fma(mp[2 * Cs], wp[2 * cs32], ch[2]);
+                    if (k < n_last) ch[3] = fma(mp[3 * Cs], wp[3 * cs32], ch[3]);
+                }
+#pragma unroll
+                for (int q = 0; q < GIBBS_NW; ++q) mid[q] = ch[q];
+#pragma unroll 4
+                for (int k = half; k < Cs; ++k, ++mp, wp += 32)
+                {
+                    ch[0] = fma(mp[0], wp[0], ch[0]);
+                    ch[1] = fma(mp[Cs], wp[cs32], ch[1]);
+                    ch[2] = fma(mp[2 * Cs], wp[2 * cs32], ch[2]);
+                    if (k < n_last) ch[3] = fma(mp[3 * Cs], wp[3 * cs32], ch[3]);
                 }
             }
             else
@@ -756,35 +786,47 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
                         if (s < S) ch[q] = fma(mass[s], wl[s * 32], ch[q]);
                     }
                 }
+#pragma unroll
+                for (int q = 0; q < GIBBS_NW; ++q) mid[q] = 0;
             }
 #pragma unroll
             for (int q = 0; q < GIBBS_NW; ++q) off[q + 1] = off[q] + ch[q];
             base_tot = off[GIBBS_NW];
             // ---- phase B: lower_bound of u*total over the cumulative weights of strains 0..S-2 (S-1 if none
-            // reaches it): the chunk first, then the chain of that chunk once more with the comparison riding along
+            // reaches it): the chunk first, then its half, then the chain of that half once more with the comparison
+            // riding along.  Cumulative weights do not decrease, so the strains below the threshold are a prefix:
+            // count them and keep the chain value of the last one; cum(c) is one more step from there.
             const double thr = u * base_tot;
             int q = 0;
 #pragma unroll
             for (int k = 1; k < GIBBS_NW; ++k) q += (off[k] < thr) ? 1 : 0;
-            double oq = 0;
+            double oq = 0, mq = mid[0];
 #pragma unroll
-            for (int k = 1; k < GIBBS_NW; ++k) oq = (q == k) ? off[k] : oq;
+            for (int k = 1; k < GIBBS_NW; ++k) { oq = (q == k) ? off[k] : oq; mq = (q == k) ? mid[k] : mq; }
             const int lo = q * Cs, end = min(lo + Cs, S - 1);  // candidates lo..end-1
-            double run = 0;
-            bool found = false;
-            int cn = lo;
-            b_prev = oq;  // cum(lo-1) is the same number as off[q]
-            for (int k = 0; k < Cs; ++k)
+            // the second half, when every strain of the first half is a candidate below the threshold
+            const bool halves = n_last >= 0 && lo + half <= end;  // else: walk the whole chunk from its start
+            const bool second = halves && (oq + mq < thr);
+            const int nk = halves ? half : Cs;
+            int cn = second ? lo + half : lo;
+            double run = second ? mq : 0.0, run_u = run;  // run_u: the chain at the last strain below the threshold
             {
-                const int s = lo + k;
-                const bool in = s < end;
-                const int sc = in ? s : 0;
-                run = fma(mass[sc], wl[sc * 32], run);
-                const double v = oq + run;
-                const bool take = in && !found;
-                const bool under = v < thr;
-                if (take && under) { b_prev = v; ++cn; }
-                if (take && !under) { b_here = v; found = true; }
+                const int s0 = cn;
+                const double* mp = mass + s0;
+                const double* wp = wl + s0 * 32;
+                for (int k = 0; k < nk; ++k)
+                {
+                    const bool in = s0 + k < end;
+                    const int kc = in ? k : 0;
+                    run = fma(mp[kc], wp[kc * 32], run);
+                    const bool under = in && (oq + run < thr);
+                    if (under) { run_u = run; ++cn; }
+                }
+            }
+            b_prev = oq + run_u;  // cum(cn-1); with nothing below it, cum(lo-1) -- the same number as off[q]
+            {
+                const int sc = min(cn, S - 1);
+                b_here = oq + fma(mass[sc], wl[sc * 32], run_u);
             }
             c = valid ? min(cn, S - 1) : -1;
         }
@@ -931,23 +973,35 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
         }
         ++rounds;
         // ---- commit: letter statistics, then the masses of the next round from the exact pick counts
+        // Every warp updates its own copy of the masses from the round's counts, so the next round starts without a
+        // barrier.  The counts of round r stay readable until every warp has passed the first barrier of round
+        // r+1; each warp wipes its own bytes of them in the commit of round r+1, before it publishes into that
+        // buffer again in round r+2.
         if (valid && g.mode == MODE_GIBBS) atomicAdd(&cnt[c * 8 + cd], 1);
         if (active && c_pub >= 0) pm[c_pub] = 0;
-        for (int s = tid; s < S; s += blockDim.x)
+        if (c_last >= 0) reinterpret_cast<unsigned char*>(hpacks + ((r + 1) & 1) * smem_S)[c_last * 8 + b] = 0;
+        c_last = active ? c_pub : -1;
+        if (lane < S)
         {
-            const unsigned long long hp = hpack[s];
+            const unsigned long long hp = hpack[lane];
             if (hp)
             {
-                const int tc = tcount[s] + (int)__dp4a((unsigned)hp, 0x01010101u, __dp4a((unsigned)(hp >> 32), 0x01010101u, 0u));
-                tcount[s] = tc;
-                mass[s] = mass0[s] + (double)tc;
-                hpack[s] = 0;
+                tc0 += (int)__dp4a((unsigned)hp, 0x01010101u, __dp4a((unsigned)(hp >> 32), 0x01010101u, 0u));
+                mass[lane] = mass0[lane] + (double)tc0;
             }
         }
-        __syncthreads();
-        if (blk_next == 0) ++sweep;
-        blk = blk_next;
+        if (lane + 32 < S)
+        {
+            const unsigned long long hp = hpack[lane + 32];
+            if (hp)
+            {
+                tc1 += (int)__dp4a((unsigned)hp, 0x01010101u, __dp4a((unsigned)(hp >> 32), 0x01010101u, 0u));
+                mass[lane + 32] = mass0[lane + 32] + (double)tc1;
+            }
+        }
+        __syncwarp();
     }
+    __syncthreads();  // the letter counts of every warp
     if (tid == 0 && counters)
     {
         atomicAdd(&counters[0], rounds);
@@ -1019,7 +1073,7 @@ static void launch_gibbs(const StepLaunch& L, int smem_S, cudaStream_t st)
 // dynamic shared memory of k_gibbs_w<NB>
 static size_t gibbs_w_smem_bytes(int nb, int smem_S)
 {
-    return 8 * ((size_t)64 * nb * smem_S + 3 * (size_t)smem_S + 2 + (size_t)nb * GIBBS_LIST) + 4 * ((size_t)nb * smem_S + 9 * (size_t)smem_S);
+    return 8 * ((size_t)64 * nb * smem_S + (size_t)(nb + 3) * smem_S + 2 + (size_t)nb * GIBBS_LIST) + 4 * ((size_t)nb * smem_S + 8 * (size_t)smem_S);
 }
 
 template <int NB>

@@ -231,16 +231,15 @@ struct Engine
     double tau, diff, e;
     // step staging
     std::vector<StepGroup> h_groups;
-    PinBuf<StepGroup> p_groups;
-    PinBuf<int> p_I;
-    PinBuf<double> p_D, p_al;
+    PinBuf<char> p_arena;   // the step's staged inputs: [doubles | step groups | ints]
+    size_t off_groups = 0, off_I = 0, arena_bytes = 0;
+    PinBuf<double> p_al;
     size_t n_I = 0, n_D = 0;
     std::vector<InheritOp> h_ops;
     std::vector<int> group_sub;
     std::unique_ptr<Workers> workers;
-    DevBuf<StepGroup> d_groups;
-    DevBuf<int> d_I;
-    DevBuf<double> d_D, d_W, d_U;
+    DevBuf<char> d_arena;
+    DevBuf<double> d_W, d_U;
     DevBuf<InheritOp> d_ops;
     DevBuf<unsigned long long> d_counters;
     DevBuf<double> ll_arena, sub_arena;
@@ -647,12 +646,18 @@ struct Engine
         }
         n_I = ti;
         n_D = td;
-        p_I.reserve(std::max<size_t>(ti, 1));
-        p_D.reserve(std::max<size_t>(td, 1));
+        // one pinned arena per step -- [doubles | step groups | ints], each part 16-byte aligned -- so that a
+        // level costs one host-to-device copy
+        off_groups = (sizeof(double) * td + 15) & ~size_t(15);
+        off_I = (off_groups + sizeof(StepGroup) * h_groups.size() + 15) & ~size_t(15);
+        arena_bytes = off_I + sizeof(int) * ti;
+        p_arena.reserve(std::max<size_t>(arena_bytes, 16));
+        int* const pI = reinterpret_cast<int*>(p_arena.p + off_I);
+        double* const pD = reinterpret_cast<double*>(p_arena.p);
         auto copy_one = [&](size_t k) {
             const Sub& s = subs[group_sub[k]];
-            if (!s.I.empty()) memcpy(p_I.p + at_i[k], s.I.data(), sizeof(int) * s.I.size());
-            if (!s.Dv.empty()) memcpy(p_D.p + at_d[k], s.Dv.data(), sizeof(double) * s.Dv.size());
+            if (!s.I.empty()) memcpy(pI + at_i[k], s.I.data(), sizeof(int) * s.I.size());
+            if (!s.Dv.empty()) memcpy(pD + at_d[k], s.Dv.data(), sizeof(double) * s.Dv.size());
         };
         if (workers && group_sub.size() >= 8) workers->run(group_sub.size(), copy_one);
         else for (size_t k = 0; k < group_sub.size(); ++k) copy_one(k);
@@ -676,7 +681,8 @@ struct Engine
             RAMBL_CUDA(cudaMemcpyAsync(d_ops.p, h_ops.data() + b, sizeof(InheritOp) * n, cudaMemcpyHostToDevice, st));
             stats.h2d_bytes += (long long)sizeof(InheritOp) * n;
             launch_inherit(d_ops.p, n, max_stride, st, &stats.launches);
-            RAMBL_CUDA(cudaStreamSynchronize(st));  // h_ops / d_ops are reused
+            // no synchronisation: h_ops is pageable (the copy has left it when cudaMemcpyAsync returns) and a
+            // second chunk reuses d_ops in stream order
         }
         h_ops.clear();
     }
@@ -702,18 +708,15 @@ struct Engine
             any_hard = any_hard || sg.mode == MODE_HARD;
             any_gibbs = any_gibbs || sg.mode == MODE_GIBBS || sg.mode == MODE_ASSIGN;
         }
-        d_groups.reserve(h_groups.size());
-        d_I.reserve(std::max<size_t>(1, n_I));
-        d_D.reserve(std::max<size_t>(1, n_D));
+        d_arena.reserve(std::max<size_t>(arena_bytes, 16));
         d_W.reserve(std::max<long long>(1, w_total));
-        p_groups.reserve(h_groups.size());
         p_al.reserve(std::max<size_t>(1, n_D));
-        memcpy(p_groups.p, h_groups.data(), sizeof(StepGroup) * h_groups.size());
-        RAMBL_CUDA(cudaMemcpyAsync(d_groups.p, p_groups.p, sizeof(StepGroup) * h_groups.size(), cudaMemcpyHostToDevice, st));
-        if (n_I) RAMBL_CUDA(cudaMemcpyAsync(d_I.p, p_I.p, sizeof(int) * n_I, cudaMemcpyHostToDevice, st));
-        if (n_D) RAMBL_CUDA(cudaMemcpyAsync(d_D.p, p_D.p, sizeof(double) * n_D, cudaMemcpyHostToDevice, st));
+        memcpy(p_arena.p + off_groups, h_groups.data(), sizeof(StepGroup) * h_groups.size());
+        RAMBL_CUDA(cudaMemcpyAsync(d_arena.p, p_arena.p, arena_bytes, cudaMemcpyHostToDevice, st));
+        double* const dD = reinterpret_cast<double*>(d_arena.p);
         StepLaunch L;
-        L.groups = d_groups.p; L.n_groups = (int)h_groups.size(); L.iarena = d_I.p; L.darena = d_D.p;
+        L.groups = reinterpret_cast<const StepGroup*>(d_arena.p + off_groups); L.n_groups = (int)h_groups.size();
+        L.iarena = reinterpret_cast<const int*>(d_arena.p + off_I); L.darena = dD;
         L.weights = d_W.p; L.uniforms = d_U.p; L.n_uniforms = kUniforms; L.counters = d_counters.p;
         L.max_S = max_S; L.max_m = max_m; L.max_D = max_D; L.any_hard = any_hard; L.any_gibbs = any_gibbs;
         if (any_gibbs)
@@ -733,7 +736,7 @@ struct Engine
         stats.h2d_bytes += (long long)(sizeof(StepGroup) * h_groups.size() + sizeof(int) * n_I + sizeof(double) * n_D);
         stats.d2h_bytes += (long long)(sizeof(double) * n_D);
         launch_level_step(L, st, &stats.launches);
-        RAMBL_CUDA(cudaMemcpyAsync(p_al.p, d_D.p, sizeof(double) * n_D, cudaMemcpyDeviceToHost, st));
+        RAMBL_CUDA(cudaMemcpyAsync(p_al.p, dD, sizeof(double) * n_D, cudaMemcpyDeviceToHost, st));
         RAMBL_CUDA(cudaStreamSynchronize(st));
         stats.level_steps += 1;
         return p_al.p;
