@@ -620,7 +620,7 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
 }
 
 // The same chain with ONE warp per 32-draw block and up to eight blocks (256 draws) per round, for levels of
-// at most 64 candidate strains (the reference prunes to about 80 and usually holds 10-50).  A warp keeps its
+// at most 128 candidate strains (the reference prunes to about 80 and usually holds 10-50).  A warp keeps its
 // block to itself -- no partial sums to exchange, no barriers inside a block -- and spends about a third of
 // the instructions per draw of k_gibbs, which is what bounds a round once several warps share a scheduler:
 //   * cumulative weights are not stored: phase A forms the four chunk totals (four independent fma chains),
@@ -634,16 +634,16 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
 //   * a pick that fails its check is re-derived by its warp, candidate strain s on lane s % 32, with the same
 //     sums in the same order, so check and re-derivation cannot disagree.
 // cum(s) = off[chunk of s] + (fma chain from the start of that chunk), as in k_gibbs.
-constexpr int GIBBS_LIST = 72;  // 64 strains + padding
-
-template <int NB>
+// NS = strains per lane in the per-warp bookkeeping: 2 for levels of up to 64 strains, 4 for up to 128
+template <int NB, int NS>
 __global__ void __launch_bounds__(32 * NB, 1)
 k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, double* __restrict__ Dar,
           double* __restrict__ W, const double* __restrict__ U, unsigned long long* counters, int smem_S)
 {
     const StepGroup g = groups[blockIdx.x];
     if (g.mode != MODE_GIBBS && g.mode != MODE_ASSIGN) return;
-    extern __shared__ __align__(128) double gibbs_smem[];  // sized for the largest S of the launch (smem_S <= 64)
+    constexpr int GIBBS_LIST = 32 * NS + 8;  // every strain + padding
+    extern __shared__ __align__(128) double gibbs_smem[];  // sized for the largest S of the launch (smem_S <= 32*NS)
     double* wbuf = gibbs_smem;                       // [2][block][strain][lane] weights of a round (bulk-copied)
     double* masses = wbuf + 2 * NB * smem_S * 32;    // [block][smem_S] masses at the start of the round, one copy per warp
     double* mass0 = masses + NB * smem_S;            // [smem_S] masses at the start of the launch
@@ -702,7 +702,9 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
     const unsigned below_lo = (unsigned)below, below_hi = (unsigned)(below >> 32);
     const unsigned lt = (1u << lane) - 1u;
     double* mass = masses + b * smem_S;  // this warp's copy: a round ends without a barrier (see the commit)
-    int tc0 = 0, tc1 = 0;                // picks of strains lane and lane+32 since the launch began
+    int tc[NS];                          // picks of strains lane, lane+32, .. since the launch began
+#pragma unroll
+    for (int h = 0; h < NS; ++h) tc[h] = 0;
     int c_last = -1;                     // this lane's final pick of the previous round
     unsigned* pm = pmask + b * smem_S;
     uint2* list = lists + b * GIBBS_LIST;
@@ -855,18 +857,24 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
                 // the strains that count for this block (picked in an earlier block or on a lane of this one), in
                 // strain order, as a list of (strain, picks in earlier blocks, lanes of this block): lane i looks at
                 // strains i and i+32; the list is padded to a multiple of four with entries that add nothing
-                int n_list;
+                int n_list = 0;
                 {
-                    const bool in0 = lane < S, in1 = lane + 32 < S;
-                    const unsigned long long hp0 = in0 ? hpack[lane] : 0ull, hp1 = in1 ? hpack[lane + 32] : 0ull;
-                    const unsigned mm0 = in0 ? pm[lane] : 0u, mm1 = in1 ? pm[lane + 32] : 0u;
-                    const unsigned hs0 = __dp4a((unsigned)hp0 & below_lo, 0x01010101u, __dp4a((unsigned)(hp0 >> 32) & below_hi, 0x01010101u, 0u));
-                    const unsigned hs1 = __dp4a((unsigned)hp1 & below_lo, 0x01010101u, __dp4a((unsigned)(hp1 >> 32) & below_hi, 0x01010101u, 0u));
-                    const unsigned bal0 = __ballot_sync(full, (hs0 | mm0) != 0), bal1 = __ballot_sync(full, (hs1 | mm1) != 0);
-                    const int n0 = __popc(bal0);
-                    n_list = n0 + __popc(bal1);
-                    if (hs0 | mm0) list[__popc(bal0 & lt)] = make_uint2((unsigned)lane | (hs0 << 8), mm0);
-                    if (hs1 | mm1) list[n0 + __popc(bal1 & lt)] = make_uint2((unsigned)(lane + 32) | (hs1 << 8), mm1);
+                    unsigned hs[NS], mm[NS];
+#pragma unroll
+                    for (int h = 0; h < NS; ++h)
+                    {
+                        const bool in = lane + 32 * h < S;
+                        const unsigned long long hp = in ? hpack[lane + 32 * h] : 0ull;
+                        mm[h] = in ? pm[lane + 32 * h] : 0u;
+                        hs[h] = __dp4a((unsigned)hp & below_lo, 0x01010101u, __dp4a((unsigned)(hp >> 32) & below_hi, 0x01010101u, 0u));
+                    }
+#pragma unroll
+                    for (int h = 0; h < NS; ++h)
+                    {
+                        const unsigned bal = __ballot_sync(full, (hs[h] | mm[h]) != 0);
+                        if (hs[h] | mm[h]) list[n_list + __popc(bal & lt)] = make_uint2((unsigned)(lane + 32 * h) | (hs[h] << 8), mm[h]);
+                        n_list += __popc(bal);
+                    }
                     if (lane < 4) list[n_list + lane] = make_uint2(0u, 0u);
                     __syncwarp();
                 }
@@ -981,22 +989,18 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
         if (active && c_pub >= 0) pm[c_pub] = 0;
         if (c_last >= 0) reinterpret_cast<unsigned char*>(hpacks + ((r + 1) & 1) * smem_S)[c_last * 8 + b] = 0;
         c_last = active ? c_pub : -1;
-        if (lane < S)
+#pragma unroll
+        for (int h = 0; h < NS; ++h)
         {
-            const unsigned long long hp = hpack[lane];
-            if (hp)
+            const int sh = lane + 32 * h;
+            if (sh < S)
             {
-                tc0 += (int)__dp4a((unsigned)hp, 0x01010101u, __dp4a((unsigned)(hp >> 32), 0x01010101u, 0u));
-                mass[lane] = mass0[lane] + (double)tc0;
-            }
-        }
-        if (lane + 32 < S)
-        {
-            const unsigned long long hp = hpack[lane + 32];
-            if (hp)
-            {
-                tc1 += (int)__dp4a((unsigned)hp, 0x01010101u, __dp4a((unsigned)(hp >> 32), 0x01010101u, 0u));
-                mass[lane + 32] = mass0[lane + 32] + (double)tc1;
+                const unsigned long long hp = hpack[sh];
+                if (hp)
+                {
+                    tc[h] += (int)__dp4a((unsigned)hp, 0x01010101u, __dp4a((unsigned)(hp >> 32), 0x01010101u, 0u));
+                    mass[sh] = mass0[sh] + (double)tc[h];
+                }
             }
         }
         __syncwarp();
@@ -1073,20 +1077,28 @@ static void launch_gibbs(const StepLaunch& L, int smem_S, cudaStream_t st)
 // dynamic shared memory of k_gibbs_w<NB>
 static size_t gibbs_w_smem_bytes(int nb, int smem_S)
 {
-    return 8 * ((size_t)64 * nb * smem_S + (size_t)(nb + 3) * smem_S + 2 + (size_t)nb * GIBBS_LIST) + 4 * ((size_t)nb * smem_S + 8 * (size_t)smem_S);
+    const size_t list = smem_S <= 64 ? 72 : 136;  // GIBBS_LIST of the NS the launcher picks
+    return 8 * ((size_t)64 * nb * smem_S + (size_t)(nb + 3) * smem_S + 2 + (size_t)nb * list) + 4 * ((size_t)nb * smem_S + 8 * (size_t)smem_S);
 }
 
-template <int NB>
-static void launch_gibbs_w(const StepLaunch& L, int smem_S, cudaStream_t st)
+template <int NB, int NS>
+static void launch_gibbs_w_ns(const StepLaunch& L, int smem_S, cudaStream_t st)
 {
     const size_t smem = gibbs_w_smem_bytes(NB, smem_S);
     static size_t configured = 0;
     if (smem > configured)
     {
-        RAMBL_CUDA(cudaFuncSetAttribute(k_gibbs_w<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RAMBL_CUDA(cudaFuncSetAttribute(k_gibbs_w<NB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    k_gibbs_w<NB><<<L.n_groups, 32 * NB, smem, st>>>(L.groups, L.iarena, L.darena, L.weights, L.uniforms, L.counters, smem_S);
+    k_gibbs_w<NB, NS><<<L.n_groups, 32 * NB, smem, st>>>(L.groups, L.iarena, L.darena, L.weights, L.uniforms, L.counters, smem_S);
+}
+
+template <int NB>
+static void launch_gibbs_w(const StepLaunch& L, int smem_S, cudaStream_t st)
+{
+    if (smem_S <= 64) launch_gibbs_w_ns<NB, 2>(L, smem_S, st);
+    else launch_gibbs_w_ns<NB, 4>(L, smem_S, st);
 }
 
 void set_gibbs_blocks(int blocks) { g_gibbs_blocks = blocks; }
@@ -1116,10 +1128,10 @@ void launch_level_step(const StepLaunch& L, cudaStream_t st, int* launches)
         const int smem_S = (L.max_S + 3) & ~3;
         // 32-draw blocks per round: a few subgroups leave SMs idle, so their chains go wide (as far as the
         // shared memory of one SM carries S strains); a batch of hundreds fills the SMs with narrow CTAs,
-        // several per SM.  Levels of at most 64 strains take the warp-per-block kernel, wider ones the
+        // several per SM.  Levels of at most 128 strains take the warp-per-block kernel, wider ones the
         // four-warps-per-block kernel.  The chain -- and so every result -- is the same for any choice.
         int nb = 8;
-        bool warp_per_block = L.max_S <= 64;
+        bool warp_per_block = L.max_S <= 128;
         if (g_gibbs_blocks > 0) nb = g_gibbs_blocks;
         if (g_gibbs_blocks < 0) { nb = -g_gibbs_blocks; warp_per_block = false; }
         if (warp_per_block)

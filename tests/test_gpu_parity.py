@@ -272,6 +272,15 @@ def test_full_size_properties(cfg):
     b1, b2 = _solve([sg]), _solve([sg])
     assert b1.status(0) == api.RAMBL_OK
     assert b1.strains_text(0) == b2.strains_text(0)
+    # ... and the chain does not depend on how many draws a round speculates over: the default (warp-per-block
+    # kernel, up to 256 draws per round at ~48 candidate strains) against the four-warps-per-block kernel at
+    # 32 draws per round (the configuration checked against the reference at depth 800) and against 64
+    try:
+        for blocks in (-1, 2):
+            assert api.lib().rambl_set_gibbs_blocks(blocks) == api.RAMBL_OK
+            assert _solve([sg]).strains_text(0) == b1.strains_text(0), blocks
+    finally:
+        api.lib().rambl_set_gibbs_blocks(0)
     st = b1.strains(0)
     assert abs(sum(s.abundance for s in st) - 1.0) < 1e-9
     nodes = refpy.parse_graph_dump(b1.graph_dump(0))
