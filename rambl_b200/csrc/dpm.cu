@@ -8,6 +8,7 @@
 // and the parity tests check paths, assignments and abundances against the oracle).
 #include "dpm.cuh"
 
+#include <algorithm>
 #include <cmath>
 
 #include "common.hpp"
@@ -141,6 +142,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+constexpr int WEIGHTS_UNROLL = 4;
+
 __global__ void __launch_bounds__(128) k_weights(const StepGroup* __restrict__ groups, const int* __restrict__ I,
                                                  double* __restrict__ W)
 {
@@ -151,14 +154,24 @@ __global__ void __launch_bounds__(128) k_weights(const StepGroup* __restrict__ g
     const int mate = I[g.draw_off + g.D + d];
     const int rid = I[g.rid_off + r];
     double* w = group_weights(W, g);
-    for (int s = 0; s < g.S; ++s)
+    // blockIdx.z strides over the strains: a single subgroup has few draws per level, and one thread walking
+    // all S strains is S dependent gathers in a row
+    double v[WEIGHTS_UNROLL];
+    for (int s0 = blockIdx.z * WEIGHTS_UNROLL; s0 < g.S; s0 += gridDim.z * WEIGHTS_UNROLL)
     {
-        const double* row = g.ll + (long long)I[g.slot_off + s] * g.ll_stride;
-        double v = row[rid];
-        if (mate >= 0) v += row[mate];
-        w[weight_index(d, s, g.S)] = exp(v);
+#pragma unroll
+        for (int k = 0; k < WEIGHTS_UNROLL; ++k)
+        {
+            const int s = min(s0 + k, g.S - 1);
+            const double* row = g.ll + (long long)I[g.slot_off + s] * g.ll_stride;
+            v[k] = row[rid];
+            if (mate >= 0) v[k] += row[mate];
+        }
+#pragma unroll
+        for (int k = 0; k < WEIGHTS_UNROLL; ++k)
+            if (s0 + k < g.S) w[weight_index(d, s0 + k, g.S)] = exp(v[k]);
     }
-    if (g.mode == MODE_GIBBS)
+    if (g.mode == MODE_GIBBS && blockIdx.z == 0)
     {
         const int rl = I[g.rid_off + 2 * g.m + r];
         group_codes(W, g)[d] = (rl == 1) ? letter_code(g.pool_chars[I[g.rid_off + g.m + r]]) : 7;
@@ -1114,7 +1127,11 @@ void launch_level_step(const StepLaunch& L, cudaStream_t st, int* launches)
     }
     if (L.max_D > 0 && (L.any_hard || L.any_gibbs))
     {
-        k_weights<<<dim3((L.max_D + 127) / 128, L.n_groups), 128, 0, st>>>(L.groups, L.iarena, L.weights);
+        // enough CTAs to cover the machine: a batch of many subgroups already has them, a single one spreads its strains
+        const int d_blocks = (L.max_D + 127) / 128;
+        const int z_max = (L.max_S + WEIGHTS_UNROLL - 1) / WEIGHTS_UNROLL;
+        const int z = std::max(1, std::min(z_max, (4 * 148) / std::max(1, d_blocks * L.n_groups)));
+        k_weights<<<dim3(d_blocks, L.n_groups, z), 128, 0, st>>>(L.groups, L.iarena, L.weights);
         ++*launches;
     }
     if (L.any_hard)
