@@ -153,10 +153,10 @@ def cpu_baseline_block(window: int, cores: int = 1):
                       "16S gene, graph build + infer_strains + read_assign, %.1f s; %s" % (sg.n_reads, window, dt, FULL_SIZE_NOTE)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_gibbs launch of this workload, from the ncu --set full
-# capture summarised in profiles/r01_k_gibbs_full.txt (825 KB read, 0 written: the weight tiles once; the
-# sweeps re-read them from L2 / shared memory)
-GIBBS_DRAM_BYTES_PER_LAUNCH = 824832
+# dram__bytes_read.sum + dram__bytes_write.sum of one Gibbs-kernel launch of this workload, from the ncu --set full
+# capture summarised in profiles/r01_k_gibbs_w_full.txt (mean of the two captured launches: 838 KB and 680 KB
+# read, 0 written: the weight tiles once; the sweeps re-read them from L2 / shared memory)
+GIBBS_DRAM_BYTES_PER_LAUNCH = 758912
 
 FULL_SIZE_NOTE = ("the reference on the FULL configs[1] subgroup (8223 reads after down-sampling), measured once on one "
                   "core of the build container with oracle/_ref -O2: 805 s = 10.2 reads/s; windowed samples run faster "
