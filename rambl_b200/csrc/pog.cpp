@@ -16,6 +16,10 @@
 #include "pog.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <map>
 #include <queue>
 #include <set>
@@ -605,13 +609,32 @@ struct GraphBuilder::Impl
     {
         std::vector<int> id(V.size(), -1);
         int N = 0;
-        for (size_t h = 0; h < V.size(); ++h) if (V[h].alive) id[h] = N++;
+        size_t n_pool = 0, n_pool_chars = 0, n_out = 0, n_in = 0, n_label = 0;
+        std::vector<char> in_read_order(V.size(), 1);  // pool ids ascending (almost always: reads are threaded in order)
+        for (size_t h = 0; h < V.size(); ++h)
+        {
+            const Vertex& x = V[h];
+            if (!x.alive) continue;
+            id[h] = N++;
+            n_pool += x.pool.size(); n_out += x.out.size(); n_in += x.in.size(); n_label += x.label.size();
+            for (size_t k = 0; k < x.pool.size(); ++k)
+            {
+                n_pool_chars += x.pool[k].s.size();
+                if (k && x.pool[k].rid < x.pool[k - 1].rid) in_read_order[h] = 0;
+            }
+        }
         g = FlatGraph();
         g.n_nodes = N;
         g.n_reads = n_reads;
         g.st.reserve(N); g.level.reserve(N);
+        g.label_chars.reserve(n_label); g.label_off.reserve(N + 1);
+        g.out_to.reserve(n_out); g.out_cover.reserve(n_out); g.out_off.reserve(N + 1);
+        g.in_from.reserve(n_in); g.in_off.reserve(N + 1);
+        g.pool_rid.resize(n_pool); g.pool_cn.resize(n_pool); g.pool_off.reserve(N + 1);
+        g.pool_chars.resize(n_pool_chars); g.pool_str_off.assign(n_pool + 1, 0);
         g.label_off.assign(1, 0); g.out_off.assign(1, 0); g.in_off.assign(1, 0); g.pool_off.assign(1, 0);
-        g.pool_str_off.assign(1, 0);
+        size_t at_pool = 0, at_chars = 0;
+        std::vector<int> ids;  // the read ids of the current vertex, ascending
         for (size_t h = 0; h < V.size(); ++h)
         {
             const Vertex& x = V[h];
@@ -621,38 +644,57 @@ struct GraphBuilder::Impl
             g.label_chars.insert(g.label_chars.end(), x.label.begin(), x.label.end());
             g.label_off.push_back((int)g.label_chars.size());
             if (x.label == "$") g.end_node = id[h];
+            if (!x.out.empty())
+            {
+                ids.clear();
+                for (const PoolItem& p : x.pool) ids.push_back(p.rid);
+                if (!in_read_order[h]) std::sort(ids.begin(), ids.end());
+            }
             for (int o : x.out)
             {
                 g.out_to.push_back(id[o]);
-                g.out_cover.push_back(reads_over_edge((int)h, o));
+                g.out_cover.push_back(reads_over_edge((int)h, o, ids, in_read_order[o] != 0));
             }
             g.out_off.push_back((int)g.out_to.size());
             for (int o : x.in) g.in_from.push_back(id[o]);
             g.in_off.push_back((int)g.in_from.size());
             for (const PoolItem& p : x.pool)
             {
-                g.pool_rid.push_back(p.rid);
-                g.pool_cn.push_back(p.cn);
-                g.pool_chars.insert(g.pool_chars.end(), p.s.begin(), p.s.end());
-                g.pool_str_off.push_back((int)g.pool_chars.size());
+                g.pool_rid[at_pool] = p.rid;
+                g.pool_cn[at_pool] = p.cn;
+                const size_t len = p.s.size();
+                if (len == 1) g.pool_chars[at_chars] = p.s[0];
+                else memcpy(g.pool_chars.data() + at_chars, p.s.data(), len);
+                at_chars += len;
+                g.pool_str_off[++at_pool] = (int)at_chars;
             }
-            g.pool_off.push_back((int)g.pool_rid.size());
+            g.pool_off.push_back((int)at_pool);
         }
     }
 
     // number_of_reads_cover_nodes, PartialOrderGraph.cpp:1218-1244: sum over pairs with equal read id of
-    // the second pool's copy number; done on sorted copies of the two id lists.
-    int reads_over_edge(int hu, int hv) const
+    // the second pool's copy number.  `a` holds the first pool's ids in ascending order; a second pool that is
+    // in read order too is merged against it in one pass, any other is looked up item by item.
+    int reads_over_edge(int hu, int hv, const std::vector<int>& a, bool v_in_read_order) const
     {
         const Vertex& u = V[hu];
         const Vertex& v = V[hv];
         int n = 0;
         if (hu == 0) { for (const PoolItem& p : v.pool) n += p.cn; return n; }
         if (v.label == "$") { for (const PoolItem& p : u.pool) n += p.cn; return n; }
-        std::vector<int> a;
-        a.reserve(u.pool.size());
-        for (const PoolItem& p : u.pool) a.push_back(p.rid);
-        std::sort(a.begin(), a.end());
+        if (v_in_read_order)
+        {
+            size_t i = 0;
+            const size_t na = a.size();
+            for (const PoolItem& p : v.pool)
+            {
+                while (i < na && a[i] < p.rid) ++i;
+                size_t j = i;
+                while (j < na && a[j] == p.rid) ++j;  // i stays: the next item of v may carry the same id
+                n += (int)(j - i) * p.cn;
+            }
+            return n;
+        }
         for (const PoolItem& p : v.pool)
         {
             auto range = std::equal_range(a.begin(), a.end(), p.rid);
@@ -682,13 +724,31 @@ void GraphBuilder::finish(const MsaResult& rows, FlatGraph& out)
 {
     if (m->n_problems > 0 && (int)rows.width.size() < m->first_problem + m->n_problems)
         throw Error(RAMBL_ERR_STATE, "GraphBuilder::finish called without the solved alignment batch");
+    static const bool trace = getenv("RAMBL_TRACE") != nullptr;
+    auto t = std::chrono::steady_clock::now();
+    double ms[7];
+    int k = 0;
+    auto lap = [&] {
+        const auto n = std::chrono::steady_clock::now();
+        ms[k++] = std::chrono::duration<double, std::milli>(n - t).count();
+        t = n;
+    };
     for (const LevelPlan& lp : m->plans) m->settle_insertions(lp, rows);
+    lap();
     m->settle_deletions();
+    lap();
     m->merge_equal_neighbours(true);
     m->merge_equal_neighbours(false);
+    lap();
     m->collapse_chains();
+    lap();
     m->level_nodes();
+    lap();
     m->flatten(out);
+    lap();
+    if (trace)
+        fprintf(stderr, "[rambl] graph finish ms: insertions %.1f deletions %.1f merge %.1f collapse %.1f level %.1f flatten %.1f\n",
+                ms[0], ms[1], ms[2], ms[3], ms[4], ms[5]);
 }
 
 void fill_edge_cover(FlatGraph& g)
