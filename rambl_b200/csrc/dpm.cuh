@@ -6,7 +6,8 @@
 //   k_loglik   per-read log-likelihood update of every candidate strain   (lines 343-391)
 //   k_weights  exp(loglik(read) + loglik(mate)) per (draw, strain)        (lines 50-60, 178-191)
 //   k_hard     soft assignment + sufficient statistics + model update     (hard_clustering, 17-125)
-//   k_gibbs    sequential Gibbs sweeps + statistics + model update        (np_bayes_clustering, 127-244)
+//   k_gibbs_w  sequential Gibbs sweeps + statistics + model update        (np_bayes_clustering, 127-244)
+//   k_gibbs    the same for levels of more than 128 strains (and wide levels of big batches)
 //   k_inherit  child strains take a copy of their parent's state          (Strain copies, 505-522)
 // A "group" is one subgroup's share of the step; all groups of a step sit in one descriptor array.
 #pragma once

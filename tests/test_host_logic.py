@@ -111,6 +111,18 @@ def test_calls_in_wrong_order_are_errors():
 
 
 @pytest.mark.skipif(HAVE_GPU, reason="only meaningful on a box without a device")
+def test_gibbs_block_hook_accepts_only_the_documented_values():
+    """rambl_set_gibbs_blocks (a measurement / test hook, include/rambl_b200.h): 0 = automatic, 1/2/4/8 blocks of
+    32 draws per round, -1/-2/-4 the same on the four-warps-per-block kernel; anything else is refused."""
+    try:
+        for ok in (1, 2, 4, 8, -1, -2, -4, 0):
+            assert api.lib().rambl_set_gibbs_blocks(ok) == api.RAMBL_OK, ok
+        for bad in (3, 5, 16, -3, -8, 100):
+            assert api.lib().rambl_set_gibbs_blocks(bad) == api.RAMBL_ERR_INVALID, bad
+    finally:
+        api.lib().rambl_set_gibbs_blocks(0)
+
+
 def test_no_device_is_a_loud_error():
     with pytest.raises(api.RamblError) as ei:
         api.msa_align_batch([["ACG", "A"]])
