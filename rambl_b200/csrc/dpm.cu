@@ -637,7 +637,7 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
 // block to itself -- no partial sums to exchange, no barriers inside a block -- and spends about a third of
 // the instructions per draw of k_gibbs, which is what bounds a round once several warps share a scheduler:
 //   * cumulative weights are not stored: phase A forms the four chunk totals (four independent fma chains),
-//     phase B re-runs the one chunk that holds u * total and keeps the two cumulative weights around the pick
+//     phase B re-runs the half chunk that holds u * total and keeps the two cumulative weights around the pick
 //     in registers (the check needs nothing else), so shared memory holds the weights only;
 //   * every pick of the round is published as a per-strain count (byte b of hpack = block b) and, for the
 //     block's own lanes, a per-strain lane mask; draw j of block b is corrected by
