@@ -175,6 +175,24 @@ struct GraphBuilder::Impl
         for (char c : G) { int w = add(ST_MAT, c); connect(u, w); u = w; }
         connect(u, add(ST_MAT, '$'));
         const int last = backbone + 1;
+        {
+            // backbone pools grow to the coverage of their position: size them once (difference array over the
+            // reads' reference spans) instead of doubling their way up
+            std::vector<int> cover(G.size() + 2, 0);
+            for (const AlignedRead& rd : R)
+            {
+                if (rd.pos < 0 || rd.pos >= last) continue;  // refused below
+                const int hi = (int)std::min<size_t>(G.size(), (size_t)rd.pos + rd.seq.size());
+                ++cover[rd.pos];
+                --cover[hi];
+            }
+            int depth = 0;
+            for (size_t i = 0; i < G.size(); ++i)
+            {
+                depth += cover[i];
+                if (depth > 0) V[i + 1].pool.reserve((size_t)depth);
+            }
+        }
 
         for (int rid = 0; rid < (int)R.size(); ++rid)
         {
