@@ -62,6 +62,10 @@ void rambl_release_cached_memory(void);
  * that otherwise serves only levels of more than 64 strains.  Every setting computes the same chain -- this
  * is a measurement and test hook, not a results knob.  Returns RAMBL_ERR_INVALID for any other value. */
 int rambl_set_gibbs_blocks(int32_t blocks);
+/* Host worker threads for the per-subgroup host work (graph construction, staging).  0 = $RAMBL_HOST_THREADS if
+ * set, else one per hardware thread.  scripts/rambl.py's `--cores` (rambl.py:179) is the natural value; several
+ * processes sharing a box (one per GPU) should each take their share. */
+int rambl_set_host_threads(int32_t n);
 
 /* ---- MultipleSequenceAlignmentSP<Index2D,SimpleScoreModel,vector,string,char>::align
  *      (MultipleSequenceAlignment.hpp:87-107, MultipleSequenceAlignmentSP.cpp:10-301), batched.

@@ -85,9 +85,7 @@ template <typename F>
 void parallel_for(size_t lo, size_t hi, F&& fn)
 {
     const size_t n = hi > lo ? hi - lo : 0;
-    unsigned nt = std::thread::hardware_concurrency();
-    if (nt == 0) nt = 1;
-    nt = (unsigned)std::min<size_t>(std::min<size_t>(nt, 64), n);
+    unsigned nt = (unsigned)std::min<size_t>(std::min<size_t>(host_threads(), 64), n);
     if (nt <= 1)
     {
         for (size_t i = lo; i < hi; ++i) fn(i);
@@ -220,6 +218,13 @@ int rambl_set_gibbs_blocks(int32_t blocks)
     return RAMBL_OK;
 }
 
+int rambl_set_host_threads(int32_t n)
+{
+    if (n < 0) return RAMBL_ERR_INVALID;
+    set_host_threads(n);
+    return RAMBL_OK;
+}
+
 int64_t rambl_msa_rows_capacity(int32_t P, const int32_t* prob_seq_off, const int32_t* seq_off)
 {
     int64_t total = 0;
@@ -332,8 +337,27 @@ int rambl_batch_add_graph(rambl_batch* b, int32_t n_nodes, int32_t n_reads, cons
             g.pool_chars.assign(pool_chars, pool_chars + pool_str_off[ne]);
         }
         else g.pool_str_off.assign(1, 0);
+        auto monotone = [&](const std::vector<int>& off, const char* what) {
+            if (off[0] != 0) throw Error(RAMBL_ERR_INVALID, std::string(what) + " must start at 0");
+            for (size_t i = 1; i < off.size(); ++i)
+                if (off[i] < off[i - 1]) throw Error(RAMBL_ERR_INVALID, std::string(what) + " must not decrease");
+        };
+        monotone(g.label_off, "label_off");
+        monotone(g.out_off, "out_off");
+        monotone(g.pool_off, "pool_off");
+        monotone(g.pool_str_off, "pool_str_off");
+        if (out_off[n_nodes] > 0 && !out_to) throw Error(RAMBL_ERR_INVALID, "out_to is null");
         for (int v : g.out_to) if (v < 0 || v >= n_nodes) throw Error(RAMBL_ERR_INVALID, "edge target out of range");
-        for (int r : g.pool_rid) if (r < 0 || r >= n_reads) throw Error(RAMBL_ERR_INVALID, "read id out of range");
+        for (int r = 0; r < n_reads; ++r)
+            if (read_copies[r] < 1) throw Error(RAMBL_ERR_INVALID, "copy number must be >= 1");
+        for (int e2 = 0; e2 < ne; ++e2)
+        {
+            const int r = g.pool_rid[e2];
+            if (r < 0 || r >= n_reads) throw Error(RAMBL_ERR_INVALID, "read id out of range");
+            // a pool entry draws once per copy and looks its mate up by copy index (NonparametricClustering.cpp:169-189)
+            if (g.pool_cn[e2] < 1 || g.pool_cn[e2] > read_copies[r])
+                throw Error(RAMBL_ERR_INVALID, "pool_copies must lie in [1, read_copies[read]]");
+        }
         for (int u = 0; u < n_nodes; ++u)
             if (g.label_off[u + 1] - g.label_off[u] == 1 && g.label_chars[g.label_off[u]] == '$') g.end_node = u;
         if (g.label(0) != "^" || g.end_node < 0) throw Error(RAMBL_ERR_INVALID, "node 0 must be '^' and one node must be '$'");

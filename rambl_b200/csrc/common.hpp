@@ -95,4 +95,10 @@ struct PinBuf
 
 void require_device();  // throws RAMBL_ERR_CUDA when no B200-class device is present
 
+// Host worker threads this process may use for the per-subgroup host work (graph construction, staging):
+// rambl_set_host_threads(), else $RAMBL_HOST_THREADS, else the hardware concurrency.  Several ranks on one box
+// each take their share of the cores instead of all spawning one worker per core.
+unsigned host_threads();
+void set_host_threads(int n);
+
 }  // namespace rambl

@@ -576,7 +576,12 @@ k_gibbs(const StepGroup* __restrict__ groups, const int* __restrict__ I, double*
             // draw 32b+j is final after 32b+j+1 passes, so 32*NG+1 passes always suffice -- the cap only guards
             // the device against a launch that does not terminate
             const int any_moved = __syncthreads_or(moved ? 1 : 0);  // also orders this pass before the next publication
-            if (!any_moved || ++settle_passes > 32 * NG + 8) break;
+            if (!any_moved) break;
+            if (++settle_passes > 32 * NG + 8)
+            {   // cannot happen for finite weights; report it instead of committing a round that is not the chain
+                if (tid == 0 && counters) atomicAdd(&counters[2], 1ull);
+                break;
+            }
         }
         ++rounds;
         // ---- commit: letter statistics, then the masses of the next round from the exact pick counts
@@ -990,7 +995,12 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
             // draw 32b+j is final after 32b+j+1 passes, so 32*NB+1 passes always suffice -- the cap only guards
             // the device against a launch that does not terminate
             const int any_moved = __syncthreads_or(moved ? 1 : 0);  // also orders this pass before the next publication
-            if (!any_moved || ++settle_passes > 32 * NB + 8) break;
+            if (!any_moved) break;
+            if (++settle_passes > 32 * NB + 8)
+            {   // cannot happen for finite weights; report it instead of committing a round that is not the chain
+                if (tid == 0 && counters) atomicAdd(&counters[2], 1ull);
+                break;
+            }
         }
         ++rounds;
         // ---- commit: letter statistics, then the masses of the next round from the exact pick counts

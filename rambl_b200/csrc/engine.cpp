@@ -235,7 +235,6 @@ struct Engine
     size_t off_groups = 0, off_I = 0, arena_bytes = 0;
     PinBuf<double> p_al;
     size_t n_I = 0, n_D = 0;
-    std::vector<InheritOp> h_ops;
     std::vector<int> group_sub;
     std::unique_ptr<Workers> workers;
     DevBuf<char> d_arena;
@@ -299,8 +298,8 @@ struct Engine
         subs.resize(in.size());
         std::vector<double> u = canonical_stream(kUniforms);
         d_U.reserve(kUniforms);
-        d_counters.reserve(2);
-        RAMBL_CUDA(cudaMemsetAsync(d_counters.p, 0, 2 * sizeof(unsigned long long), st));
+        d_counters.reserve(4);
+        RAMBL_CUDA(cudaMemsetAsync(d_counters.p, 0, 4 * sizeof(unsigned long long), st));
         RAMBL_CUDA(cudaMemcpyAsync(d_U.p, u.data(), sizeof(double) * kUniforms, cudaMemcpyHostToDevice, st));
         for (size_t i = 0; i < in.size(); ++i)
         {
@@ -365,8 +364,9 @@ struct Engine
     // ---- "$": read_reassign's sort + merge_strains, NonparametricClustering.cpp:309-315,645-702 ----
     void close_result(Sub& s)
     {
-        std::vector<Cand> v = s.cands;
-        if (v.empty()) { s.status = RAMBL_ERR_NO_STRAINS; s.have_result = true; s.result.clear(); return; }
+        if (s.cands.empty()) { s.status = RAMBL_ERR_NO_STRAINS; s.have_result = true; s.result.clear(); return; }
+        std::vector<Cand> v;
+        v.swap(s.cands);
         sort_desc_by_abundance(v);
         sort_desc_by_abundance(v);  // merge_strains sorts again
         std::vector<Cand> merged(1, v[0]);
@@ -378,8 +378,12 @@ struct Engine
             for (; j < merged.size(); ++j)
                 if (sequence_identity(q, mseq[j]) > 1 - diff) { merged[j].ab += v[i].ab; break; }
             if (j == merged.size()) { merged.push_back(v[i]); mseq.push_back(q); }
+            else give_slot(s, v[i].slot);  // merged away: the level goes on without it
         }
-        // the reference copies the strains here; later levels (if any) must not touch the copies
+        // the reference sorts and merges level_strains in place (lines 309-315): any level after this one
+        // continues from the merged set
+        s.cands = merged;
+        // ... and copies the strains out; later levels (if any) must not touch the copies
         for (Cand& c : s.result) if (c.slot >= 0) { s.retained[c.slot] = 0; s.free_slots.push_back(c.slot); }
         for (Cand& c : merged)
         {
@@ -495,6 +499,7 @@ struct Engine
             }
         if (s.mode == MODE_HARD)  // Strain::logprob(uid) creates the entry (line 57)
             for (int k = 0; k < D; ++k) if (dm[k] >= 0) s.present[dm[k]] = 1;
+        if (D <= 0) throw Error(RAMBL_ERR_INVALID, "a read-pool entry without copies");
         sg.nsweeps = (s.mode == MODE_GIBBS) ? std::min(prm.n, 40000 / D) : 0;
         sg.ab_off = (int)h_D.size();
         for (const Cand& c : s.cands) h_D.push_back(c.ab);
@@ -663,28 +668,46 @@ struct Engine
         else for (size_t k = 0; k < group_sub.size(); ++k) copy_one(k);
     }
 
+    // Slot copies queued since the last flush.  The copies of one launch run in no defined order, so a copy that
+    // reads or overwrites a slot an EARLIER queued copy writes or reads (a candidate taken at "$" right after it
+    // was created as a second child, say) waits for the next launch: ops are dealt into waves by dependency.
     void flush_inherits()
     {
+        std::vector<std::vector<InheritOp>> waves;
+        std::vector<int> wave_of;
         for (size_t i = 0; i < subs.size(); ++i)
         {
             Sub& s = subs[i];
-            for (const auto& c : s.ops) h_ops.push_back({s.ll.p, (long long)s.R, s.sub.p, c.first, c.second});
+            wave_of.assign(s.ops.size(), 0);
+            for (size_t a = 0; a < s.ops.size(); ++a)
+            {
+                int w = 0;
+                for (size_t b = 0; b < a; ++b)
+                {
+                    const bool raw = s.ops[b].second == s.ops[a].first;   // reads what b writes
+                    const bool waw = s.ops[b].second == s.ops[a].second;  // overwrites what b writes
+                    const bool war = s.ops[b].first == s.ops[a].second;   // overwrites what b reads
+                    if (raw || waw || war) w = std::max(w, wave_of[b] + 1);
+                }
+                wave_of[a] = w;
+                if ((int)waves.size() <= w) waves.resize(w + 1);
+                waves[w].push_back({s.ll.p, (long long)s.R, s.sub.p, s.ops[a].first, s.ops[a].second});
+            }
             s.ops.clear();
             stats.launches += s.local_launches;
             s.local_launches = 0;
         }
-        if (h_ops.empty()) return;
-        for (size_t b = 0; b < h_ops.size(); b += 32768)
-        {
-            const int n = (int)std::min<size_t>(32768, h_ops.size() - b);
-            d_ops.reserve(n);
-            RAMBL_CUDA(cudaMemcpyAsync(d_ops.p, h_ops.data() + b, sizeof(InheritOp) * n, cudaMemcpyHostToDevice, st));
-            stats.h2d_bytes += (long long)sizeof(InheritOp) * n;
-            launch_inherit(d_ops.p, n, max_stride, st, &stats.launches);
-            // no synchronisation: h_ops is pageable (the copy has left it when cudaMemcpyAsync returns) and a
-            // second chunk reuses d_ops in stream order
-        }
-        h_ops.clear();
+        for (const std::vector<InheritOp>& ops : waves)
+            for (size_t b = 0; b < ops.size(); b += 32768)
+            {
+                const int n = (int)std::min<size_t>(32768, ops.size() - b);
+                d_ops.reserve(n);
+                RAMBL_CUDA(cudaMemcpyAsync(d_ops.p, ops.data() + b, sizeof(InheritOp) * n, cudaMemcpyHostToDevice, st));
+                stats.h2d_bytes += (long long)sizeof(InheritOp) * n;
+                launch_inherit(d_ops.p, n, max_stride, st, &stats.launches);
+                // the staging vector is pageable (the copy has left it when cudaMemcpyAsync returns) and a
+                // second chunk reuses d_ops in stream order
+            }
     }
 
     const double* run_step()
@@ -752,11 +775,12 @@ struct Engine
             cudaEventDestroy(gibbs_events[k + 1]);
         }
         gibbs_events.clear();
-        unsigned long long c[2] = {0, 0};
+        unsigned long long c[4] = {0, 0, 0, 0};
         if (d_counters.p && cudaMemcpy(c, d_counters.p, sizeof c, cudaMemcpyDeviceToHost) == cudaSuccess)
         {
             stats.gibbs_rounds += (long long)c[0];
             stats.gibbs_passes += (long long)c[1];
+            if (c[2]) throw Error(RAMBL_ERR_CUDA, "internal error: a Gibbs round did not settle (non-finite weights?)");
         }
     }
 
@@ -851,8 +875,7 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
     E.start(in);
     const double ms_start = since(w0);
     {
-        unsigned nt = std::thread::hardware_concurrency();
-        nt = std::min<unsigned>(nt ? nt : 1, 32);
+        const unsigned nt = std::min<unsigned>(host_threads(), 32);
         if (E.subs.size() >= 4 && nt > 1) E.workers.reset(new Workers(std::min<size_t>(nt, E.subs.size())));
     }
     double trace[4] = {0, 0, 0, 0};

@@ -1,6 +1,9 @@
 // Process-wide cache of device and pinned-host allocations (see common.hpp).
+#include <atomic>
+#include <cstdlib>
 #include <map>
 #include <mutex>
+#include <thread>
 
 #include "common.hpp"
 
@@ -94,6 +97,27 @@ void release_cached_memory()
     }
     for (auto& kv : d) cudaFree(kv.second);
     for (auto& kv : h) cudaFreeHost(kv.second);
+}
+
+}  // namespace rambl
+
+namespace rambl {
+
+static std::atomic<int> g_host_threads{0};
+
+void set_host_threads(int n) { g_host_threads.store(n > 0 ? n : 0); }
+
+unsigned host_threads()
+{
+    int n = g_host_threads.load();
+    if (n <= 0)
+    {
+        const char* e = getenv("RAMBL_HOST_THREADS");
+        if (e) n = atoi(e);
+    }
+    if (n <= 0) n = (int)std::thread::hardware_concurrency();
+    if (n <= 0) n = 1;
+    return (unsigned)std::min(n, 256);
 }
 
 }  // namespace rambl

@@ -341,6 +341,16 @@ def write_cli_fixture(dirname: str, gene_name: str, gene: str, raw) -> Tuple[str
 
 
 # Named workloads of BASELINE.json["configs"] ------------------------------------------------
+def config2_subgroup(k: int, window: Optional[Tuple[int, int]] = None) -> Subgroup:
+    """Subgroup k of BASELINE configs[2] ("500 synthetic taxonomic subgroups x 5k reads"): 5 000 150 bp reads from
+    2-6 strains of the 16S gene.  With ``window`` the same subgroup restricted to a slice of the gene at the same
+    depth (the read count shrinks with the slice) -- the bounded samples the CPU reference is timed on."""
+    if window is None:
+        return make_subgroup(5000, 150, 2 + (k % 5), seed=k)
+    w = window[1] - window[0]
+    return make_subgroup(max(50, int(5000 * w / 1542)), min(150, w), 2 + (k % 5), seed=k, window=window)
+
+
 def config_workload(idx: int, seed: int = 0, scale: float = 1.0) -> List[Subgroup]:
     """BASELINE.json configs[idx] as a list of subgroups (scale<1 shrinks read counts for tests)."""
     if idx == 0:  # 2k 100bp reads from 3 mutated strains (CPU-runnable)
@@ -349,7 +359,7 @@ def config_workload(idx: int, seed: int = 0, scale: float = 1.0) -> List[Subgrou
         return [make_subgroup(int(20000 * scale), 150, 10, divergence=(0.01, 0.03), seed=seed)]
     if idx == 2:  # 500 subgroups x 5k reads
         n = max(1, int(500 * scale))
-        return [make_subgroup(5000, 150, 2 + (k % 5), seed=seed * 100003 + k) for k in range(n)]
+        return [config2_subgroup(seed * 100003 + k) for k in range(n)]
     if idx == 3:  # one deep subgroup, 1M 150bp reads, 50 strains (down-sampled to -D like StrainCall)
         return [make_subgroup(int(1000000 * scale), 150, 50, divergence=(0.01, 0.03), seed=seed)]
     if idx == 4:  # 250bp MiSeq-like reads, indel-rich strains with homopolymer errors

@@ -17,6 +17,12 @@ def load_golden(name):
         return json.load(f)
 
 
+def load_golden_gz(name):
+    import gzip
+    with gzip.open(os.path.join(ROOT, "tests", "golden", name), "rt") as f:
+        return json.load(f)
+
+
 def strip_sib(txt):
     """Graph dump without the SIB field (sibling lists keep ids of deleted nodes in the reference)."""
     out = []

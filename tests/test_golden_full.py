@@ -1,0 +1,40 @@
+"""CPU: the full-size golden fixtures (tests/golden/full_*.json.gz, the unmodified reference's output on the bench
+workloads) are present, well-formed, and belong to the inputs bench.py generates today -- rambl_b200.synth must
+reproduce every stored input bit for bit from the stored spec, else the GPU parity test at benchmark size would be
+checking a different workload than the one that is timed."""
+import os
+
+import pytest
+
+from helpers import ROOT, load_golden_gz
+from rambl_b200 import synth
+
+CASES = ["config0_seed0", "config1_seed0", "config2_sub0", "config2_sub3", "config2_sub4"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_full_golden_belongs_to_todays_workload(name):
+    path = os.path.join(ROOT, "tests", "golden", "full_%s.json.gz" % name)
+    assert os.path.exists(path), "run tools/make_golden_full.py in the build container"
+    case = load_golden_gz("full_%s.json.gz" % name)
+    spec = dict(case["spec"])
+    if "divergence" in spec:
+        spec["divergence"] = tuple(spec["divergence"])
+    sg = synth.make_subgroup(**spec)
+    inp = case["input"]
+    assert sg.gene == inp["gene"] and sg.pos == inp["pos"] and sg.cigar == inp["cigar"] and sg.seq == inp["seq"]
+    assert sg.cn == inp["cn"]
+    assert [int(x) for x in sg.pair_off] == inp["pair_off"] and [int(x) for x in sg.pair_val] == inp["pair_val"]
+    assert case["n_reads"] == sg.n_reads and case["n_raw_reads"] == sg.n_raw_reads
+    st = case["strains"]
+    assert set(st) == {"infer", "assign", "final"} and len(st["final"]) >= 1
+    assert abs(sum(s["abundance"] for s in st["final"]) - 1.0) < 1e-9
+    assert case["reference_seconds"]["infer_and_assign"] > 10  # minutes of CPU: why these are fixtures, not live runs
+
+
+def test_bench_workload_definitions_match_the_golden_specs():
+    """bench.py's configs[2] subgroup k and configs[1] block are the calls the fixtures were generated with."""
+    c = load_golden_gz("full_config2_sub3.json.gz")
+    assert c["spec"] == dict(n_reads=5000, read_len=150, n_strains=2 + 3 % 5, seed=3)
+    sg = synth.config2_subgroup(3)
+    assert sg.seq == c["input"]["seq"] and sg.pos == c["input"]["pos"]

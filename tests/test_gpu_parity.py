@@ -6,8 +6,8 @@ import pytest
 from oracle import refpy
 from rambl_b200 import api, synth
 
-from helpers import (REL_TOL, compare_strains, fuzz_spec, load_golden, msa_fuzz_problems, normalise_golden_strains,
-                     strip_sib, subgroup_from_golden)
+from helpers import (REL_TOL, compare_strains, fuzz_spec, load_golden, load_golden_gz, msa_fuzz_problems,
+                     normalise_golden_strains, strip_sib, subgroup_from_golden)
 
 pytestmark = pytest.mark.gpu
 
@@ -244,12 +244,10 @@ def test_config4_like_indel_rich_250bp_reads(n, ie, W):
 
 
 def test_depth800_sample_of_configs1_matches_reference():
-    """The bounded sample bench.py times the reference on (configs[1] restricted to a 160 bp window: depth 800,
-    150 bp reads, 10 strains, ~840 reads, 50 sweeps of ~800 draws per level) -- the deepest case the reference
-    finishes in seconds.  Strain paths, order, consensus and abundances against the real reference when
-    oracle/_ref is present (else the oracle)."""
-    import bench
-    sg = bench.make_cpu_sample(160, 0)
+    """configs[1] restricted to a 160 bp window (depth 800, 150 bp reads, 10 strains, ~840 reads, 50 sweeps of ~800
+    draws per level) -- the deepest case the reference finishes in seconds.  Strain paths, order, consensus and
+    abundances against the real reference when oracle/_ref is present (else the oracle)."""
+    sg = synth.make_subgroup(int(20000 * 160 / 1542), 150, 10, divergence=(0.01, 0.03), seed=0, window=(600, 760))
     variant = "" if refpy.available("") else "oracle"
     o = refpy.RefPog(sg.gene, sg.pos, sg.cigar, sg.seq, sg.cn, variant=variant)
     want, _ = o.infer(sg.pair_off, sg.pair_val)
@@ -259,6 +257,46 @@ def test_depth800_sample_of_configs1_matches_reference():
     got = refpy.parse_strain_dump(b.strains_text(0))
     assert compare_strains(want, got) == []
     assert b.stats()["draws"] > 1000000
+
+
+def test_matched_sample_set_of_the_bench_matches_reference():
+    """The sample set bench.py's reference arm times (configs[2] subgroups on a gene window) solved as ONE batch,
+    subgroup by subgroup against the reference (oracle/_ref when present, else the oracle): the like-for-like pair
+    of the bench line is also a parity case."""
+    import bench
+    w, sgs = bench.matched_sample_set(20)
+    b = _solve(sgs)
+    variant = "" if refpy.available("") else "oracle"
+    for i, sg in enumerate(sgs[:6]):
+        o = refpy.RefPog(sg.gene, sg.pos, sg.cigar, sg.seq, sg.cn, variant=variant)
+        want, _ = o.infer(sg.pair_off, sg.pair_val)
+        assert b.status(i) == api.RAMBL_OK
+        got = refpy.parse_strain_dump(b.strains_text(i))
+        assert compare_strains(want, got) == [], i
+
+
+FULL_GOLDEN = ["config0_seed0", "config1_seed0", "config2_sub0", "config2_sub3", "config2_sub4"]
+
+
+@pytest.mark.parametrize("name", FULL_GOLDEN)
+def test_full_size_matches_golden_reference(name):
+    """BASELINE configs[0], configs[1] (the single-chain bench block) and whole-gene subgroups of configs[2] (the bench
+    workload) at FULL size against what the unmodified reference produced for the same inputs
+    (tests/golden/full_*.json.gz, generated by tools/make_golden_full.py; the reference needs 1-13 minutes per case):
+    graph (node dump and output_edge text by hash), strain paths, order, consensus, abundances, substitution tables
+    and every per-read log-likelihood."""
+    import hashlib
+    case = load_golden_gz("full_%s.json.gz" % name)
+    sg = subgroup_from_golden(case["input"])
+    b = _solve([sg])
+    assert b.status(0) == api.RAMBL_OK
+    assert b.num_nodes(0) == case["n_nodes"]
+    assert hashlib.sha256(strip_sib(b.graph_dump(0)).encode()).hexdigest() == case["dump_nosib_sha256"]
+    assert hashlib.sha256(b.output_edge(0).encode()).hexdigest() == case["edges_sha256"]
+    got = refpy.parse_strain_dump(b.strains_text(0))
+    want = normalise_golden_strains(case["strains"])
+    assert compare_strains(want, got) == []
+    assert [s["path"] for s in want["final"]] == [s["path"] for s in got["final"]]
 
 
 @pytest.mark.parametrize("cfg", [0, 1])
