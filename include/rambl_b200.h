@@ -49,6 +49,9 @@ typedef struct rambl_stats
     int64_t gibbs_alg_bytes;  /* sweeps x draws x (S weights + 1 uniform) x 8 bytes over those launches */
     int64_t gibbs_rounds;     /* rounds of 32 speculative draws, and the passes it took to settle them */
     int64_t gibbs_passes;
+    float dpm_kernel_ms;      /* CUDA-event time of the device-resident strain walk (one kernel, one CTA per subgroup) */
+    int32_t dpm_launches;
+    int64_t dpm_alg_bytes;    /* its algorithmic bytes: Gibbs bytes + 16 B per log-likelihood update + 16 B per weight */
 } rambl_stats;
 
 const char* rambl_last_error(void);
@@ -62,6 +65,12 @@ void rambl_release_cached_memory(void);
  * that otherwise serves only levels of more than 64 strains.  Every setting computes the same chain -- this
  * is a measurement and test hook, not a results knob.  Returns RAMBL_ERR_INVALID for any other value. */
 int rambl_set_gibbs_blocks(int32_t blocks);
+/* The strain search of rambl_batch_infer runs as ONE kernel that walks every subgroup's graph levels on the device
+ * (mode 1, the default).  Mode 0 keeps the level-synchronous path only (host decisions between levels), which also
+ * solves the subgroups the walk kernel cannot take.  rambl_set_walk_blocks pins the warps per subgroup of the walk
+ * kernel (1, 2, 4, 8; 0 = by batch size).  Both paths compute the same chains: measurement and test hooks. */
+int rambl_set_walk_mode(int32_t mode);
+int rambl_set_walk_blocks(int32_t blocks);
 /* Host worker threads for the per-subgroup host work (graph construction, staging).  0 = $RAMBL_HOST_THREADS if
  * set, else one per hardware thread.  scripts/rambl.py's `--cores` (rambl.py:179) is the natural value; several
  * processes sharing a box (one per GPU) should each take their share. */

@@ -39,7 +39,8 @@ class Stats(C.Structure):
                 ("loglik_updates", C.c_int64), ("msa_dp_cells", C.c_int64), ("msa_problems", C.c_int32),
                 ("msa_kernel_ms", C.c_float), ("infer_gpu_ms", C.c_float), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("gibbs_kernel_ms", C.c_float), ("gibbs_launches", C.c_int32),
-                ("gibbs_alg_bytes", C.c_int64), ("gibbs_rounds", C.c_int64), ("gibbs_passes", C.c_int64)]
+                ("gibbs_alg_bytes", C.c_int64), ("gibbs_rounds", C.c_int64), ("gibbs_passes", C.c_int64),
+                ("dpm_kernel_ms", C.c_float), ("dpm_launches", C.c_int32), ("dpm_alg_bytes", C.c_int64)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -56,6 +57,8 @@ SYMBOLS = {
     "rambl_release_cached_memory": (None, []),
     "rambl_set_gibbs_blocks": (C.c_int, [C.c_int32]),
     "rambl_set_host_threads": (C.c_int, [C.c_int32]),
+    "rambl_set_walk_mode": (C.c_int, [C.c_int32]),
+    "rambl_set_walk_blocks": (C.c_int, [C.c_int32]),
     "rambl_msa_rows_capacity": (C.c_int64, [C.c_int32, _i32p, _i32p]),
     "rambl_msa_sp_align_batch": (C.c_int, [C.c_int32, _i32p, _i32p, C.c_char_p, _i32p, _i64p, _i32p, C.c_char_p,
                                            C.POINTER(C.c_uint64), C.POINTER(C.c_float)]),

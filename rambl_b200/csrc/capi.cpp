@@ -218,6 +218,20 @@ int rambl_set_gibbs_blocks(int32_t blocks)
     return RAMBL_OK;
 }
 
+int rambl_set_walk_mode(int32_t mode)
+{
+    if (mode != 0 && mode != 1) return RAMBL_ERR_INVALID;
+    set_walk_mode(mode);
+    return RAMBL_OK;
+}
+
+int rambl_set_walk_blocks(int32_t blocks)
+{
+    if (blocks != 0 && blocks != 1 && blocks != 2 && blocks != 4 && blocks != 8) return RAMBL_ERR_INVALID;
+    set_walk_blocks(blocks);
+    return RAMBL_OK;
+}
+
 int rambl_set_host_threads(int32_t n)
 {
     if (n < 0) return RAMBL_ERR_INVALID;
@@ -495,6 +509,9 @@ int rambl_batch_infer(rambl_batch* b, int32_t n, float e, float tau, float diff,
         b->stats.gibbs_alg_bytes += es.gibbs_bytes;
         b->stats.gibbs_rounds += es.gibbs_rounds;
         b->stats.gibbs_passes += es.gibbs_passes;
+        b->stats.dpm_kernel_ms += es.walk_ms;
+        b->stats.dpm_launches += es.walk_launches;
+        b->stats.dpm_alg_bytes += es.walk_bytes;
         b->last = prm;
     });
 }

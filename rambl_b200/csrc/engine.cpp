@@ -17,6 +17,7 @@
 #include <thread>
 
 #include "dpm.cuh"
+#include "walk.cuh"
 
 namespace rambl {
 
@@ -362,7 +363,7 @@ struct Engine
     }
 
     // ---- "$": read_reassign's sort + merge_strains, NonparametricClustering.cpp:309-315,645-702 ----
-    void close_result(Sub& s)
+    void close_result(Sub& s, bool copy_out = true)
     {
         if (s.cands.empty()) { s.status = RAMBL_ERR_NO_STRAINS; s.have_result = true; s.result.clear(); return; }
         std::vector<Cand> v;
@@ -385,13 +386,14 @@ struct Engine
         s.cands = merged;
         // ... and copies the strains out; later levels (if any) must not touch the copies
         for (Cand& c : s.result) if (c.slot >= 0) { s.retained[c.slot] = 0; s.free_slots.push_back(c.slot); }
-        for (Cand& c : merged)
-        {
-            const int k = take_slot(s);
-            inherit(s, c.slot, k);
-            c.slot = k;
-            s.retained[k] = 1;
-        }
+        if (copy_out)
+            for (Cand& c : merged)
+            {
+                const int k = take_slot(s);
+                inherit(s, c.slot, k);
+                c.slot = k;
+                s.retained[k] = 1;
+            }
         s.result = merged;
         s.have_result = true;
         s.status = RAMBL_OK;
@@ -837,9 +839,359 @@ struct Engine
         pack_step();
         return run_step();
     }
+
+    // ---- the device-resident walk (walk.cu): level tables, one launch, results -------------------------------
+    struct WalkPlan  // host side of one subgroup's tables
+    {
+        bool eligible = false;
+        int n_levels = 0, max_m = 0, max_D = 0;
+        bool multi = false;                  // some read-pool entry has more than one letter
+        std::vector<int> order;              // nodes in walk order (levels concatenated)
+        std::vector<int> lvl_ent_off;        // [n_levels + 1]
+        long long n_ent = 0, n_chars = 0;
+        // offsets into the static arena (bytes) and the scratch arena (bytes)
+        size_t o_label_off = 0, o_out_off = 0, o_out_to = 0, o_out_cover = 0, o_lvl = 0, o_rid = 0, o_cn = 0, o_soff = 0,
+               o_len = 0, o_chars = 0, o_pair_off = 0, o_pair_val = 0;
+        size_t d_present = 0, d_free = 0, d_cand0 = 0, d_cand1 = 0, d_trail = 0, d_W = 0, d_doff = 0, d_dent = 0, d_dmate = 0,
+               d_fresh = 0, d_ab = 0, d_ops = 0, d_kid = 0, d_res = 0, d_paths = 0, d_fslot = 0, d_fab = 0;
+        int trail_cap = 0;
+    };
+    std::vector<WalkPlan> plans;
+    PinBuf<char> p_static;
+    DevBuf<char> d_static, d_scratch;
+    DevBuf<WalkSub> d_walk;
+    DevBuf<WalkResult> d_walk_res;
+    DevBuf<int> d_final_slot;
+    DevBuf<double> d_final_ab;
+
+    // The walk order of prepare() -- cur = {0}; next = the unseen successors of cur, in order -- is a property of the
+    // graph.  The device walk takes a subgroup when every node sits on exactly one level, "$" ends the walk alone on
+    // the last level, a read has at most one entry per level (the log-likelihood update is then a plain add in a fixed
+    // order) and the entries fit the compact tables; anything else goes through the level-synchronous path.
+    void plan_walk(size_t i)
+    {
+        const Sub& s = subs[i];
+        WalkPlan& p = plans[i];
+        const FlatGraph& g = *s.g;
+        p = WalkPlan();
+        if (g.n_nodes < 2 || g.end_node < 0) return;
+        std::vector<int> level_of(g.n_nodes, -1);
+        std::vector<int> cur(1, 0), nxt;
+        std::vector<int> seen_rid(std::max(1, g.n_reads), -1);
+        p.lvl_ent_off.assign(1, 0);
+        int level = 0;
+        bool ok = true, ended = false;
+        while (!cur.empty() && ok)
+        {
+            if (ended) { ok = false; break; }  // something follows "$"
+            long long m = 0, D = 0;
+            nxt.clear();
+            for (int u : cur)
+            {
+                if (level_of[u] >= 0) { ok = false; break; }
+                level_of[u] = level;
+                if (u == g.end_node) { if (cur.size() != 1) ok = false; ended = true; }
+                else if (u != 0)
+                    for (int e = g.pool_off[u]; e < g.pool_off[u + 1]; ++e)
+                    {
+                        const int rid = g.pool_rid[e], cn = g.pool_cn[e], len = g.pool_str_off[e + 1] - g.pool_str_off[e];
+                        if (seen_rid[rid] == level || cn < 1 || cn > 255 || len < 1 || len > 255) { ok = false; break; }
+                        seen_rid[rid] = level;
+                        if (len > 1) p.multi = true;
+                        m += 1; D += cn; p.n_chars += len;
+                    }
+                else if (g.pool_off[1] != g.pool_off[0]) ok = false;  // "^" carries no reads
+                if (!ok) break;
+                p.order.push_back(u);
+                for (int e = g.out_off[u]; e < g.out_off[u + 1]; ++e)
+                {
+                    const int v = g.out_to[e];
+                    if (level_of[v] == -1) { level_of[v] = -2 - level; nxt.push_back(v); }
+                    else if (level_of[v] != -2 - level) { ok = false; break; }  // reached again from another level
+                }
+            }
+            if (!ok) break;
+            for (int v : nxt) level_of[v] = -1;
+            p.n_ent += m;
+            p.lvl_ent_off.push_back((int)p.n_ent);
+            p.max_m = std::max<long long>(p.max_m, m);
+            p.max_D = std::max<long long>(p.max_D, D);
+            if (D > 40000 * 8 || p.n_ent > 0x7fffff00LL) { ok = false; break; }
+            cur.swap(nxt);
+            level += 1;
+        }
+        if (!ok || !ended || level < 2) return;
+        const SubgroupInput& in = *s.in;
+        for (int v : in.pair_val) if (v >= s.R) return;  // reported by the level-synchronous path
+        p.n_levels = level;
+        p.eligible = true;
+    }
+
+    static size_t up16(size_t b) { return (b + 15) & ~size_t(15); }
+
+    // Returns the number of subgroups handed to the device walk; on return their Sub holds the closed result.
+    int run_walk(int forced_nb, int forced_tile)
+    {
+        const size_t n = subs.size();
+        plans.assign(n, WalkPlan());
+        auto each = [&](const std::function<void(size_t)>& fn) {
+            if (workers) workers->run(n, fn);
+            else for (size_t i = 0; i < n; ++i) fn(i);
+        };
+        each([&](size_t i) { plan_walk(i); });
+        std::vector<int> take;
+        size_t stat_bytes = 0, scr_bytes = 0;
+        for (size_t i = 0; i < n; ++i)
+        {
+            WalkPlan& p = plans[i];
+            if (!p.eligible) continue;
+            const Sub& s = subs[i];
+            const FlatGraph& g = *s.g;
+            const SubgroupInput& in = *s.in;
+            take.push_back((int)i);
+            auto put = [&](size_t& off, size_t bytes) { off = stat_bytes; stat_bytes += up16(bytes); };
+            put(p.o_label_off, sizeof(int) * (g.n_nodes + 1));
+            put(p.o_out_off, sizeof(int) * (g.n_nodes + 1));
+            put(p.o_out_to, sizeof(int) * g.out_to.size());
+            put(p.o_out_cover, sizeof(int) * g.out_to.size());
+            put(p.o_lvl, sizeof(int) * p.lvl_ent_off.size());
+            put(p.o_rid, sizeof(unsigned) * p.n_ent);
+            put(p.o_cn, (size_t)p.n_ent);
+            if (p.multi) { put(p.o_soff, sizeof(unsigned) * p.n_ent); put(p.o_len, (size_t)p.n_ent); }
+            put(p.o_chars, (size_t)p.n_chars);
+            put(p.o_pair_off, sizeof(int) * in.pair_off.size());
+            put(p.o_pair_val, sizeof(int) * in.pair_val.size());
+            auto scr = [&](size_t& off, size_t bytes) { off = scr_bytes; scr_bytes += up16(bytes) + 112; scr_bytes &= ~size_t(127); };
+            p.trail_cap = p.n_levels * 160 + 2048;
+            const size_t Dp = ((size_t)p.max_D + 31) & ~size_t(31);
+            scr(p.d_present, (size_t)s.R);
+            scr(p.d_free, sizeof(int) * s.slot_cap);
+            scr(p.d_cand0, sizeof(WalkCand) * WALK_KMAX);
+            scr(p.d_cand1, sizeof(WalkCand) * WALK_KMAX);
+            scr(p.d_trail, sizeof(int2) * (size_t)p.trail_cap);
+            scr(p.d_W, sizeof(double) * ((size_t)WALK_SMAX * Dp + 2 * (size_t)p.max_D + 64));
+            scr(p.d_doff, sizeof(int) * ((size_t)p.max_m + 1));
+            scr(p.d_dent, sizeof(int) * (size_t)std::max(1, p.max_D));
+            scr(p.d_dmate, sizeof(int) * (size_t)std::max(1, p.max_D));
+            scr(p.d_fresh, (size_t)std::max(1, p.max_m));
+            scr(p.d_ab, sizeof(double) * WALK_SMAX);
+            scr(p.d_ops, sizeof(int2) * WALK_KMAX);
+            scr(p.d_kid, sizeof(double) * WALK_KMAX);
+            scr(p.d_paths, sizeof(int) * (size_t)WALK_SMAX * p.n_levels);
+        }
+        if (take.empty()) return 0;
+        // ---- fill the static tables (pinned) on the workers, one copy to the device
+        p_static.reserve(stat_bytes);
+        d_static.reserve(stat_bytes);
+        d_scratch.reserve(scr_bytes);
+        d_walk_res.reserve(take.size());
+        d_final_slot.reserve(take.size() * WALK_SMAX);
+        d_final_ab.reserve(take.size() * WALK_SMAX);
+        char* const H = p_static.p;
+        auto fill = [&](size_t k) {
+            const size_t i = (size_t)take[k];
+            const WalkPlan& p = plans[i];
+            const Sub& s = subs[i];
+            const FlatGraph& g = *s.g;
+            const SubgroupInput& in = *s.in;
+            memcpy(H + p.o_label_off, g.label_off.data(), sizeof(int) * (g.n_nodes + 1));
+            memcpy(H + p.o_out_off, g.out_off.data(), sizeof(int) * (g.n_nodes + 1));
+            if (!g.out_to.empty())
+            {
+                memcpy(H + p.o_out_to, g.out_to.data(), sizeof(int) * g.out_to.size());
+                memcpy(H + p.o_out_cover, g.out_cover.data(), sizeof(int) * g.out_to.size());
+            }
+            memcpy(H + p.o_lvl, p.lvl_ent_off.data(), sizeof(int) * p.lvl_ent_off.size());
+            unsigned* rid = reinterpret_cast<unsigned*>(H + p.o_rid);
+            unsigned char* cn = reinterpret_cast<unsigned char*>(H + p.o_cn);
+            unsigned* soff = p.multi ? reinterpret_cast<unsigned*>(H + p.o_soff) : nullptr;
+            unsigned char* len = p.multi ? reinterpret_cast<unsigned char*>(H + p.o_len) : nullptr;
+            char* chars = H + p.o_chars;
+            size_t at = 0, at_c = 0;
+            for (int u : p.order)
+            {
+                if (u == 0 || u == g.end_node) continue;
+                for (int e = g.pool_off[u]; e < g.pool_off[u + 1]; ++e, ++at)
+                {
+                    rid[at] = (unsigned)g.pool_rid[e];
+                    cn[at] = (unsigned char)g.pool_cn[e];
+                    const int l = g.pool_str_off[e + 1] - g.pool_str_off[e];
+                    if (soff) { soff[at] = (unsigned)at_c; len[at] = (unsigned char)l; }
+                    if (l == 1) chars[at_c] = g.pool_chars[g.pool_str_off[e]];
+                    else memcpy(chars + at_c, g.pool_chars.data() + g.pool_str_off[e], (size_t)l);
+                    at_c += (size_t)l;
+                }
+            }
+            memcpy(H + p.o_pair_off, in.pair_off.data(), sizeof(int) * in.pair_off.size());
+            if (!in.pair_val.empty()) memcpy(H + p.o_pair_val, in.pair_val.data(), sizeof(int) * in.pair_val.size());
+        };
+        if (workers && take.size() >= 4) workers->run(take.size(), fill);
+        else for (size_t k = 0; k < take.size(); ++k) fill(k);
+        RAMBL_CUDA(cudaMemcpyAsync(d_static.p, H, stat_bytes, cudaMemcpyHostToDevice, st));
+        stats.h2d_bytes += (long long)stat_bytes;
+        // ---- descriptors
+        std::vector<WalkSub> hs(take.size());
+        char* const Dst = d_static.p;
+        char* const Dsc = d_scratch.p;
+        int max_levels = 0;
+        for (size_t k = 0; k < take.size(); ++k)
+        {
+            const size_t i = (size_t)take[k];
+            const WalkPlan& p = plans[i];
+            const Sub& s = subs[i];
+            WalkSub& w = hs[k];
+            memset(&w, 0, sizeof w);
+            w.label_off = reinterpret_cast<const int*>(Dst + p.o_label_off);
+            w.label_chars = s.d_label;
+            w.out_off = reinterpret_cast<const int*>(Dst + p.o_out_off);
+            w.out_to = reinterpret_cast<const int*>(Dst + p.o_out_to);
+            w.out_cover = reinterpret_cast<const int*>(Dst + p.o_out_cover);
+            w.end_node = s.g->end_node;
+            w.n_levels = p.n_levels;
+            w.lvl_ent_off = reinterpret_cast<const int*>(Dst + p.o_lvl);
+            w.ent_rid = reinterpret_cast<const unsigned*>(Dst + p.o_rid);
+            w.ent_cn = reinterpret_cast<const unsigned char*>(Dst + p.o_cn);
+            w.ent_soff = p.multi ? reinterpret_cast<const unsigned*>(Dst + p.o_soff) : nullptr;
+            w.ent_len = p.multi ? reinterpret_cast<const unsigned char*>(Dst + p.o_len) : nullptr;
+            w.ent_chars = Dst + p.o_chars;
+            w.pair_off = reinterpret_cast<const int*>(Dst + p.o_pair_off);
+            w.pair_val = reinterpret_cast<const int*>(Dst + p.o_pair_val);
+            w.R = s.R;
+            w.slot_cap = s.slot_cap;
+            w.ll = s.ll.p;
+            w.sub = s.sub.p;
+            w.present = reinterpret_cast<unsigned char*>(Dsc + p.d_present);
+            w.free_slots = reinterpret_cast<int*>(Dsc + p.d_free);
+            w.cand[0] = reinterpret_cast<WalkCand*>(Dsc + p.d_cand0);
+            w.cand[1] = reinterpret_cast<WalkCand*>(Dsc + p.d_cand1);
+            w.trail = reinterpret_cast<int2*>(Dsc + p.d_trail);
+            w.trail_cap = p.trail_cap;
+            w.W = reinterpret_cast<double*>(Dsc + p.d_W);
+            w.ent_doff = reinterpret_cast<int*>(Dsc + p.d_doff);
+            w.draw_entry = reinterpret_cast<int*>(Dsc + p.d_dent);
+            w.draw_mate = reinterpret_cast<int*>(Dsc + p.d_dmate);
+            w.fresh = reinterpret_cast<unsigned char*>(Dsc + p.d_fresh);
+            w.ab_io = reinterpret_cast<double*>(Dsc + p.d_ab);
+            w.ops = reinterpret_cast<int2*>(Dsc + p.d_ops);
+            w.kid_ab = reinterpret_cast<double*>(Dsc + p.d_kid);
+            w.res = d_walk_res.p + k;
+            w.paths = reinterpret_cast<int*>(Dsc + p.d_paths);
+            w.final_slot = d_final_slot.p + k * WALK_SMAX;
+            w.final_ab = d_final_ab.p + k * WALK_SMAX;
+            RAMBL_CUDA(cudaMemsetAsync(w.present, 0, (size_t)s.R, st));
+            max_levels = std::max(max_levels, p.n_levels);
+        }
+        d_walk.reserve(hs.size());
+        RAMBL_CUDA(cudaMemcpyAsync(d_walk.p, hs.data(), sizeof(WalkSub) * hs.size(), cudaMemcpyHostToDevice, st));
+        stats.h2d_bytes += (long long)(sizeof(WalkSub) * hs.size());
+        // ---- CTA shape: as many warps (32-draw blocks per Gibbs round) as still let every subgroup be resident,
+        // then the widest weight tiles that fit (levels with more strains read their weights from L1/L2)
+        const size_t sm_bytes = 227 * 1024;
+        int nb = 8, tile = 32;
+        for (; nb > 1; nb >>= 1)
+            if (148 * (sm_bytes / walk_smem_bytes(nb, 32)) >= take.size()) break;
+        if (forced_nb > 0) nb = forced_nb;
+        {
+            const size_t want = std::max<size_t>(1, (take.size() + 147) / 148);  // CTAs per SM
+            const size_t budget = sm_bytes / std::min<size_t>(want, std::max<size_t>(1, sm_bytes / walk_smem_bytes(nb, 32)));
+            tile = 32;
+            while (tile + 8 <= WALK_SMAX && walk_smem_bytes(nb, tile + 8) <= budget) tile += 8;
+        }
+        if (forced_tile > 0) tile = forced_tile;
+        WalkParams wp;
+        wp.n = prm.n;
+        wp.tau = tau;
+        wp.uniforms = d_U.p;
+        wp.counters = d_counters.p;
+        cudaEvent_t e0, e1;
+        RAMBL_CUDA(cudaEventCreate(&e0));
+        RAMBL_CUDA(cudaEventCreate(&e1));
+        RAMBL_CUDA(cudaEventRecord(e0, st));
+        launch_walk(d_walk.p, (int)take.size(), wp, nb, tile, st, &stats.launches);
+        RAMBL_CUDA(cudaEventRecord(e1, st));
+        // ---- results
+        std::vector<WalkResult> res(take.size());
+        std::vector<int> all_slot(take.size() * WALK_SMAX);
+        std::vector<double> all_ab(take.size() * WALK_SMAX);
+        RAMBL_CUDA(cudaMemcpyAsync(res.data(), d_walk_res.p, sizeof(WalkResult) * res.size(), cudaMemcpyDeviceToHost, st));
+        RAMBL_CUDA(cudaMemcpyAsync(all_slot.data(), d_final_slot.p, sizeof(int) * all_slot.size(), cudaMemcpyDeviceToHost, st));
+        RAMBL_CUDA(cudaMemcpyAsync(all_ab.data(), d_final_ab.p, sizeof(double) * all_ab.size(), cudaMemcpyDeviceToHost, st));
+        RAMBL_CUDA(cudaStreamSynchronize(st));
+        stats.d2h_bytes += (long long)(sizeof(WalkResult) * res.size() + 12 * all_slot.size());
+        float ms = 0;
+        RAMBL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        stats.walk_ms += ms;
+        stats.walk_launches += 1;
+        stats.level_steps += max_levels;
+        if (getenv("RAMBL_TRACE"))
+            fprintf(stderr, "[rambl] device walk: %zu subgroups, %d warps per CTA, tiles of %d strains, %zu B shared, %.1f ms, "
+                            "tables %.1f MB, scratch %.1f MB\n", take.size(), nb, tile, walk_smem_bytes(nb, tile), ms,
+                    stat_bytes / 1e6, scr_bytes / 1e6);
+        std::vector<std::vector<int>> h_paths(take.size());
+        for (size_t k = 0; k < take.size(); ++k)
+        {
+            const WalkResult& r = res[k];
+            if (r.status == WALK_NOT_SETTLED) throw Error(RAMBL_ERR_CUDA, "internal error: a Gibbs round did not settle (non-finite weights?)");
+            if (r.status != WALK_DONE || r.n_cands <= 0) continue;
+            const int nl = plans[take[k]].n_levels;
+            h_paths[k].resize((size_t)r.n_cands * nl);
+            RAMBL_CUDA(cudaMemcpyAsync(h_paths[k].data(), hs[k].paths, sizeof(int) * h_paths[k].size(), cudaMemcpyDeviceToHost, st));
+            stats.d2h_bytes += (long long)(sizeof(int) * h_paths[k].size());
+        }
+        RAMBL_CUDA(cudaStreamSynchronize(st));
+        int taken = 0;
+        std::vector<size_t> redo;
+        for (size_t k = 0; k < take.size(); ++k)
+        {
+            const WalkResult& r = res[k];
+            Sub& s = subs[take[k]];
+            if (r.status >= WALK_TOO_MANY_STRAINS) { redo.push_back(take[k]); continue; }
+            stats.draws += r.draws;
+            stats.loglik_updates += r.loglik_updates;
+            stats.walk_bytes += r.gibbs_bytes + 16 * r.loglik_updates + 16 * r.weight_pairs;
+            stats.gibbs_bytes += r.gibbs_bytes;
+            s.draws += r.draws;
+            s.levels = plans[take[k]].n_levels;
+            s.done = true;
+            s.cands.clear();
+            s.trail.clear();
+            const int nl = plans[take[k]].n_levels;
+            for (int c = 0; c < r.n_cands; ++c)
+            {
+                Cand cd;
+                cd.slot = all_slot[k * WALK_SMAX + c];
+                cd.ab = all_ab[k * WALK_SMAX + c];
+                int prev = -1;
+                for (int q = 0; q < nl; ++q) { s.trail.push_back({prev, h_paths[k][(size_t)c * nl + q]}); prev = (int)s.trail.size() - 1; }
+                cd.tail = prev;
+                cd.node = s.g->end_node;
+                s.cands.push_back(cd);
+            }
+            close_result(s, false);  // "$": sort + merge_strains; the walk is over, the strains keep their slots
+            ++taken;
+        }
+        // subgroups the kernel gave up on start over on the level-synchronous path: wipe what the walk wrote
+        for (size_t i : redo)
+        {
+            Sub& s = subs[i];
+            RAMBL_CUDA(cudaMemsetAsync(s.ll.p, 0, sizeof(double) * (size_t)s.slot_cap * s.R, st));
+            launch_init_models(s.sub.p, s.slot_cap, e, st, &stats.launches);
+        }
+        if (!redo.empty() && getenv("RAMBL_TRACE"))
+            fprintf(stderr, "[rambl] device walk: %zu subgroups handed back to the level-synchronous path\n", redo.size());
+        return taken;
+    }
 };
 
 }  // namespace
+
+static int g_walk_mode = 1, g_walk_blocks = 0;
+void set_walk_mode(int mode) { g_walk_mode = mode; }
+int walk_mode() { return g_walk_mode; }
+void set_walk_blocks(int nb) { g_walk_blocks = nb; }
+int walk_blocks() { return g_walk_blocks; }
 
 std::string strain_sequence(const FlatGraph& g, const std::vector<int>& path)
 {
@@ -877,6 +1229,18 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
     {
         const unsigned nt = std::min<unsigned>(host_threads(), 32);
         if (E.subs.size() >= 4 && nt > 1) E.workers.reset(new Workers(std::min<size_t>(nt, E.subs.size())));
+    }
+    // the device-resident walk takes every subgroup it can; the level-synchronous loop below solves the rest
+    {
+        const char* ev = getenv("RAMBL_WALK");
+        const int mode = ev ? atoi(ev) : walk_mode();
+        if (mode != 0)
+        {
+            const char* enb = getenv("RAMBL_WALK_NB");
+            const char* eti = getenv("RAMBL_WALK_TILE");
+            const int taken = E.run_walk(enb ? atoi(enb) : walk_blocks(), eti ? atoi(eti) : 0);
+            if (getenv("RAMBL_TRACE")) fprintf(stderr, "[rambl] device walk solved %d of %zu subgroups, until %.1f ms\n", taken, E.subs.size(), since(w0));
+        }
     }
     double trace[4] = {0, 0, 0, 0};
     auto for_subs = [&](const std::function<void(size_t)>& fn) {

@@ -63,7 +63,17 @@ struct EngineStats
     long long gibbs_bytes = 0;     // algorithmic bytes of those launches: sweeps x draws x (S weights + 1 uniform) x 8
     long long h2d_bytes = 0, d2h_bytes = 0;
     long long gibbs_rounds = 0, gibbs_passes = 0;  // rounds of 32 speculative draws / passes needed to settle them
+    float walk_ms = 0;             // CUDA-event time of the device-resident walk kernel
+    int walk_launches = 0;
+    long long walk_bytes = 0;      // its algorithmic bytes: the Gibbs bytes + 16 B per log-likelihood update + 16 B per weight
 };
+
+// 1 (default): subgroups are solved by the device-resident walk (walk.cu) where it applies; 0: level-synchronous only
+void set_walk_mode(int mode);
+int walk_mode();
+// warps per CTA of the walk kernel (= 32-draw blocks per Gibbs round): 0 = by batch size, else 1, 2, 4 or 8
+void set_walk_blocks(int nb);
+int walk_blocks();
 
 void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, std::vector<SubgroupResult>& out,
                  EngineStats& stats, cudaStream_t stream = 0);

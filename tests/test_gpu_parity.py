@@ -216,6 +216,39 @@ def test_gibbs_block_count_does_not_change_the_chain():
     assert any(st == api.RAMBL_OK for st, _ in texts[1])
 
 
+def test_device_walk_equals_level_synchronous_path():
+    """The strain search runs as one kernel that walks all levels on the device (default) or level by level with the
+    host deciding in between (rambl_set_walk_mode(0)); with 1, 2, 4 or 8 warps per subgroup.  Same chains, same
+    arithmetic in the same order: identical text, paired reads and collapsed nodes included."""
+    sgs = [synth.make_subgroup(**fuzz_spec(s)) for s in (1, 2, 3, 5, 6, 9, 12, 15, 18, 22)]
+    sgs.append(synth.make_subgroup(n_reads=800, read_len=100, n_strains=4, seed=31, window=(300, 520)))
+    sgs.append(synth.make_subgroup(n_reads=300, read_len=30, n_strains=2, seed=4, window=(500, 580), sub_err=0.002,
+                                   paired=True, divergence=(0.03, 0.06)))
+    sgs.append(synth.make_subgroup(n_reads=60, read_len=60, n_strains=2, seed=7, window=(200, 420), sub_err=0.0,
+                                   divergence=(0.01, 0.02)))  # clean reads: long collapsed nodes
+    L = api.lib()
+    texts = {}
+    try:
+        assert L.rambl_set_walk_mode(0) == api.RAMBL_OK
+        b = _solve(sgs)
+        texts["level-synchronous"] = [(b.status(i), b.strains_text(i)) for i in range(len(sgs))]
+        assert b.stats()["dpm_launches"] == 0
+        assert L.rambl_set_walk_mode(1) == api.RAMBL_OK
+        for nb in (0, 1, 2, 4, 8):
+            assert L.rambl_set_walk_blocks(nb) == api.RAMBL_OK
+            b = _solve(sgs)
+            texts["walk/%d" % nb] = [(b.status(i), b.strains_text(i)) for i in range(len(sgs))]
+            assert b.stats()["dpm_launches"] == 1
+    finally:
+        L.rambl_set_walk_mode(1)
+        L.rambl_set_walk_blocks(0)
+    assert L.rambl_set_walk_blocks(3) == api.RAMBL_ERR_INVALID
+    for k in texts:
+        for i in range(len(sgs)):
+            assert texts[k][i] == texts["level-synchronous"][i], (k, i)
+    assert sum(1 for st, _ in texts["walk/0"] if st == api.RAMBL_OK) >= 8
+
+
 def test_paired_reads_and_copies():
     sg = synth.make_subgroup(n_reads=300, read_len=30, n_strains=2, seed=4, window=(500, 580), sub_err=0.002,
                              paired=True, divergence=(0.03, 0.06))
