@@ -56,6 +56,8 @@ typedef struct rambl_stats
 
 const char* rambl_last_error(void);
 int rambl_device_count(void);
+/* Select the CUDA device of the calling thread (cudaSetDevice); one process per GPU is the intended layout. */
+int rambl_set_device(int32_t device);
 void rambl_free(void* p); /* for every char* this library returns */
 /* Device and pinned-host buffers are cached between calls (cudaMalloc/cudaFree cost up to a second per
  * strain search); this returns the cached blocks to the driver. */

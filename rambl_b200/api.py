@@ -53,6 +53,7 @@ _strp = C.POINTER(C.c_char_p)
 SYMBOLS = {
     "rambl_last_error": (C.c_char_p, []),
     "rambl_device_count": (C.c_int, []),
+    "rambl_set_device": (C.c_int, [C.c_int32]),
     "rambl_free": (None, [C.c_void_p]),
     "rambl_release_cached_memory": (None, []),
     "rambl_set_gibbs_blocks": (C.c_int, [C.c_int32]),

@@ -206,6 +206,16 @@ int rambl_device_count(void)
     return n;
 }
 
+int rambl_set_device(int32_t device)
+{
+    return guarded([&] {
+        int n = 0;
+        RAMBL_CUDA(cudaGetDeviceCount(&n));
+        if (device < 0 || device >= n) throw Error(RAMBL_ERR_INVALID, "no such CUDA device");
+        RAMBL_CUDA(cudaSetDevice(device));
+    });
+}
+
 void rambl_free(void* p) { free(p); }
 
 void rambl_release_cached_memory(void) { release_cached_memory(); }
@@ -246,7 +256,7 @@ int64_t rambl_msa_rows_capacity(int32_t P, const int32_t* prob_seq_off, const in
     {
         int64_t letters = 0;
         for (int s = prob_seq_off[p]; s < prob_seq_off[p + 1]; ++s) letters += seq_off[s + 1] - seq_off[s];
-        const int64_t cap = std::min<int64_t>(std::max<int64_t>(letters, 1), MSA_WMAX);
+        const int64_t cap = std::max<int64_t>(letters, 1);  // a profile is never wider than its letters
         total += cap * (prob_seq_off[p + 1] - prob_seq_off[p]);
     }
     return total;

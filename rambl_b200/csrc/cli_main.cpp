@@ -32,7 +32,9 @@ namespace {
 
 struct Options  // sc_parameter, StrainCall.cpp:58-95
 {
-    std::string gene_file, mapping_file, roi;
+    std::string gene_file, mapping_file;
+    std::vector<std::string> rois;  // -r may be given several times; --roi-file FILE adds one region per line
+    int device = -1;                // --device N: the GPU this process uses (default: the current device)
     int window_size = 500, overlap_size = 100;
     float error_rate = 0.01f;
     int mapping_qual = 3, max_ins = 10, read_len = 80;
@@ -61,6 +63,9 @@ void usage()
                  "-t,--tau           only include strains with abundance level >=FLT [0.02]\n"
                  "-d,--diff-rate     only include strains with difference rate >=FLT [0.01]\n"
                  "-G,--plot-graph    print graph\n"
+                 "   --roi-file FILE one region per line; with this or several -r all regions are solved\n"
+                 "                   as one batch on the GPU (output = the separate runs, concatenated)\n"
+                 "   --device INT    CUDA device to use\n"
                  "-h,--help          print this message\n\n";
 }
 
@@ -80,7 +85,18 @@ Options parse(int argc, char** argv)
         {
             auto next = [&]() -> std::string { return (i + 1 < argc) ? std::string(argv[++i]) : std::string(); };
             if (is_opt(a, "-h", "help")) o.print_help = true;
-            else if (is_opt(a, "-r", "roi")) o.roi = next();
+            else if (is_opt(a, "-r", "roi")) o.rois.push_back(next());
+            else if (a == "--roi-file")
+            {
+                std::ifstream in(next());
+                std::string line;
+                while (std::getline(in, line))
+                {
+                    while (!line.empty() && (line.back() == '\r' || line.back() == ' ' || line.back() == '\t')) line.pop_back();
+                    if (!line.empty() && line[0] != '#') o.rois.push_back(line);
+                }
+            }
+            else if (a == "--device") o.device = std::stoi(next());
             else if (is_opt(a, "-w", "window")) o.window_size = std::stoi(next());
             else if (is_opt(a, "-e", "error-rate")) o.error_rate = std::stof(next());
             else if (is_opt(a, "-q", "map-qual")) o.mapping_qual = std::stoi(next());
@@ -255,12 +271,12 @@ void adjust_window(const Options& o, const std::string& gn, int p0, int p1, int 
 struct Window { std::string gn; int p0, p1; };
 
 // make_scan_window, StrainCall.cpp:798-848
-std::vector<Window> scan_windows(const Options& o)
+std::vector<Window> scan_windows(const Options& o, const std::string& roi)
 {
     std::vector<Window> w;
     std::string gn;
     int l, L, LL;
-    if (o.roi.empty())
+    if (roi.empty())
     {
         gn = last_gene_name(o.gene_file);
         l = 1;
@@ -268,9 +284,9 @@ std::vector<Window> scan_windows(const Options& o)
     }
     else
     {
-        gn = roi_name(o.roi);
-        l = roi_start(o.roi);
-        L = roi_end(o.roi);
+        gn = roi_name(roi);
+        l = roi_start(roi);
+        L = roi_end(roi);
         LL = gene_length(o.gene_file, gn);
     }
     std::set<int> seen;
@@ -449,7 +465,21 @@ int main(int argc, char** argv)
         std::cerr << "StrainCall (rambl_b200): no CUDA device; this build has no CPU path" << std::endl;
         return 2;
     }
-    const std::vector<Window> windows = scan_windows(o);
+    if (o.device >= 0 && o.dump_inputs.empty() && rambl_set_device(o.device) != RAMBL_OK)
+    {
+        std::cerr << "StrainCall: " << rambl_last_error() << std::endl;
+        return 2;
+    }
+    // every region of interest (the reference takes one; scripts/rambl.py starts one process per seed gene,
+    // rambl.py:179-190) -- the windows of all regions go into ONE batch, and the output is what the separate runs
+    // would print one after the other
+    std::vector<Window> windows;
+    if (o.rois.empty()) windows = scan_windows(o, "");
+    for (const std::string& roi : o.rois)
+    {
+        const std::vector<Window> w = scan_windows(o, roi);
+        windows.insert(windows.end(), w.begin(), w.end());
+    }
     if (!o.dump_inputs.empty())
     {   // host-only: the windows and the reads exactly as they would enter the graph construction
         std::ofstream out(o.dump_inputs);

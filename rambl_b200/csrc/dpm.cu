@@ -577,7 +577,7 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
     extern __shared__ __align__(128) double gibbs_smem[];  // sized for the largest S of the launch (smem_S <= 32*NS)
     GibbsShared gs;
     gs.wbuf = gibbs_smem;
-    gs.tile_S = smem_S;
+    gs.wbuf_doubles = 2 * (size_t)NB * smem_S * 32;
     gs.masses = gs.wbuf + 2 * NB * smem_S * 32;
     gs.mass0 = gs.masses + NB * smem_S;
     gs.row_S = smem_S;
@@ -593,7 +593,7 @@ k_gibbs_w(const StepGroup* __restrict__ groups, const int* __restrict__ I, doubl
     unsigned uses0 = 0u, uses1 = 0u;
     unsigned long long rounds = 0, passes = 0;
     // (the chain starts with a CTA barrier, which also publishes the barrier initialisation)
-    gibbs_w_chain<NB, NS, true>(gs, uses0, uses1, S, g.D, g.nsweeps, g.mode == MODE_GIBBS, group_weights(W, g), group_codes(W, g), U,
+    gibbs_w_chain<NB, NS, true>(gs, uses0, uses1, NB, S, g.D, g.nsweeps, g.mode == MODE_GIBBS, group_weights(W, g), group_codes(W, g), U,
                                 Dar + g.ab_off, rounds, passes, counters);
     if (tid == 0 && counters)
     {

@@ -105,7 +105,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // cum(s) = off[chunk of s] + (fma chain from the start of that chunk), as in k_gibbs.
 // NS = strains per lane in the per-warp bookkeeping: 2 for levels of up to 64 strains, 4 for up to 128
 //
-// gibbs_w_chain is the whole chain of one subgroup and level, run by a CTA of exactly NB warps.  The caller owns the
+// gibbs_w_chain is the whole chain of one subgroup and level, run by a CTA of exactly NB warps, of which the first
+// `nb` take a 32-draw block per round (the caller picks nb <= NB so that the round's tiles fit the tile buffers: a
+// level of many strains runs fewer blocks per round, as the per-level launches of k_gibbs_w do).  The caller owns the
 // shared memory (GibbsShared) and the two transaction barriers, which it initialises once per kernel; `uses` counts
 // the waits done on each barrier so far, so that the phase parity survives from one call to the next (the device
 // walk calls this once per graph level).  STAGED_ONLY: the weight tiles of a round always fit the shared tile buffers
@@ -114,8 +116,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // counts per strain.
 struct GibbsShared
 {
-    double* wbuf;                 // [2][NB * tile_S * 32] weight tiles of a round, double-buffered (bulk-copied)
-    int tile_S;                   // strains the tile buffers are sized for
+    double* wbuf;                 // [2][wbuf_doubles / 2] weight tiles of a round, double-buffered (bulk-copied)
+    size_t wbuf_doubles;          // capacity of both buffers together: a staged level needs 2 * nb * S * 32
     double* masses;               // [NB][row_S] masses at the start of the round, one copy per warp
     double* mass0;                // [row_S] masses at the start of the chain
     int row_S;                    // stride of the per-strain rows (>= S)
@@ -130,7 +132,7 @@ template <int NS>
 __host__ __device__ constexpr int gibbs_list_len() { return 32 * NS + 8; }  // every strain + padding
 
 template <int NB, int NS, bool STAGED_ONLY>
-__device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& uses0, unsigned& uses1, int S, int D, int nsweeps,
+__device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& uses0, unsigned& uses1, int nb, int S, int D, int nsweeps,
                                               bool count_letters, const double* wt, const int* code, const double* U,
                                               const double* ab_in, unsigned long long& rounds, unsigned long long& passes,
                                               unsigned long long* counters)
@@ -145,8 +147,8 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
     unsigned* const pmask = gs.pmask;
     int* const cnt = gs.cnt;
     const int smem_S = gs.row_S;
-    const size_t buf_doubles = (size_t)NB * gs.tile_S * 32;  // between the two tile buffers
-    const bool staged = STAGED_ONLY || S <= gs.tile_S;
+    const size_t buf_doubles = (size_t)nb * S * 32;  // one round's tiles: the second buffer starts right behind
+    const bool staged = STAGED_ONLY || 2 * buf_doubles <= gs.wbuf_doubles;
     const int tid = threadIdx.x, lane = tid & 31, b = tid >> 5;
     const unsigned full = 0xffffffffu;
     const int Dp = padded_draws(D);
@@ -160,18 +162,18 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
     }
     __syncthreads();
     // The chain is one stream of tiles: tile T = sweep * tiles + t holds draws 32t..32t+31 of that sweep, and round
-    // r takes tiles r*NB .. r*NB+NB-1 whatever sweep they fall in (the weights of tile t are the same in every
+    // r takes tiles r*nb .. r*nb+nb-1 whatever sweep they fall in (the weights of tile t are the same in every
     // sweep), so only the very last round can be short of blocks.
     const int tiles = Dp / 32;                       // tiles of 32 draws per sweep
     const int total_tiles = (S >= 2) ? nsweeps * tiles : 0;   // <= 5000 sweeps x 40000/32 tiles
-    const int n_rounds = (total_tiles + NB - 1) / NB;
+    const int n_rounds = (total_tiles + nb - 1) / nb;
     int stage_pos = 0;  // tile (within a sweep) the next staged round starts at; thread 0 only
     // stage the weights of round r: its tiles are contiguous up to the end of a sweep, then wrap to tile 0
     auto stage = [&](int r) {
         if (staged && tid == 0)
         {
             const int bf = r & 1;
-            int left = min(NB, total_tiles - r * NB);
+            int left = min(nb, total_tiles - r * nb);
             mbar_expect_tx(&bars[bf], (unsigned)left * (unsigned)S * 256u);
             double* dst = wbuf + (size_t)bf * buf_doubles;
             while (left > 0)
@@ -203,14 +205,14 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
     while (tiles > 0 && t_next >= tiles) { t_next -= tiles; ++sw_next; }
     double u_next = 0.0;
     int cd_next = 0;
-    if (b < total_tiles && t_next * 32 + lane < D)
+    if (b < nb && b < total_tiles && t_next * 32 + lane < D)
     {
         u_next = U[(long long)sw_next * D + t_next * 32 + lane];
         if (count_letters) cd_next = code[t_next * 32 + lane];
     }
     for (int r = 0; r < n_rounds; ++r)
     {
-        const bool active = r * NB + b < total_tiles;  // only the last round can leave the high blocks idle
+        const bool active = b < nb && r * nb + b < total_tiles;  // only the last round can leave the high blocks idle
         const int t_cur = t_next;
         const int d = t_cur * 32 + lane;
         const bool valid = active && d < D;
@@ -219,10 +221,10 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
         if (r + 1 < n_rounds)
         {
             stage(r + 1);  // overlaps this round's arithmetic
-            t_next += NB;
+            t_next += nb;
             while (t_next >= tiles) { t_next -= tiles; ++sw_next; }
             const int dn = t_next * 32 + lane;
-            const bool vn = (r + 1) * NB + b < total_tiles && dn < D;
+            const bool vn = b < nb && (r + 1) * nb + b < total_tiles && dn < D;
             u_next = vn ? U[(long long)sw_next * D + dn] : 0.0;
             cd_next = (vn && count_letters) ? code[dn] : 0;
         }

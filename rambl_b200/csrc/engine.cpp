@@ -844,6 +844,8 @@ struct Engine
     struct WalkPlan  // host side of one subgroup's tables
     {
         bool eligible = false;
+        int reason = 0;  // why not: 1 a node on two levels, 2 "$" not alone / not last, 3 a read twice on a level, 4 entry range,
+                         // 5 "^" carries reads, 6 size, 7 mate id out of range, 8 no graph
         int n_levels = 0, max_m = 0, max_D = 0;
         bool multi = false;                  // some read-pool entry has more than one letter
         std::vector<int> order;              // nodes in walk order (levels concatenated)
@@ -874,7 +876,7 @@ struct Engine
         WalkPlan& p = plans[i];
         const FlatGraph& g = *s.g;
         p = WalkPlan();
-        if (g.n_nodes < 2 || g.end_node < 0) return;
+        if (g.n_nodes < 2 || g.end_node < 0) { p.reason = 8; return; }
         std::vector<int> level_of(g.n_nodes, -1);
         std::vector<int> cur(1, 0), nxt;
         std::vector<int> seen_rid(std::max(1, g.n_reads), -1);
@@ -883,31 +885,32 @@ struct Engine
         bool ok = true, ended = false;
         while (!cur.empty() && ok)
         {
-            if (ended) { ok = false; break; }  // something follows "$"
+            if (ended) { ok = false; p.reason = 2; break; }  // something follows "$"
             long long m = 0, D = 0;
             nxt.clear();
             for (int u : cur)
             {
-                if (level_of[u] >= 0) { ok = false; break; }
+                if (level_of[u] >= 0) { ok = false; p.reason = 1; break; }
                 level_of[u] = level;
-                if (u == g.end_node) { if (cur.size() != 1) ok = false; ended = true; }
+                if (u == g.end_node) { if (cur.size() != 1) { ok = false; p.reason = 2; } ended = true; }
                 else if (u != 0)
                     for (int e = g.pool_off[u]; e < g.pool_off[u + 1]; ++e)
                     {
                         const int rid = g.pool_rid[e], cn = g.pool_cn[e], len = g.pool_str_off[e + 1] - g.pool_str_off[e];
-                        if (seen_rid[rid] == level || cn < 1 || cn > 255 || len < 1 || len > 255) { ok = false; break; }
+                        if (seen_rid[rid] == level) { ok = false; p.reason = 3; break; }
+                        if (cn < 1 || cn > 255 || len < 1 || len > 255) { ok = false; p.reason = 4; break; }
                         seen_rid[rid] = level;
                         if (len > 1) p.multi = true;
                         m += 1; D += cn; p.n_chars += len;
                     }
-                else if (g.pool_off[1] != g.pool_off[0]) ok = false;  // "^" carries no reads
+                else if (g.pool_off[1] != g.pool_off[0]) { ok = false; p.reason = 5; }  // "^" carries no reads
                 if (!ok) break;
                 p.order.push_back(u);
                 for (int e = g.out_off[u]; e < g.out_off[u + 1]; ++e)
                 {
                     const int v = g.out_to[e];
                     if (level_of[v] == -1) { level_of[v] = -2 - level; nxt.push_back(v); }
-                    else if (level_of[v] != -2 - level) { ok = false; break; }  // reached again from another level
+                    else if (level_of[v] != -2 - level) { ok = false; p.reason = 1; break; }  // reached again from another level
                 }
             }
             if (!ok) break;
@@ -916,13 +919,13 @@ struct Engine
             p.lvl_ent_off.push_back((int)p.n_ent);
             p.max_m = std::max<long long>(p.max_m, m);
             p.max_D = std::max<long long>(p.max_D, D);
-            if (D > 40000 * 8 || p.n_ent > 0x7fffff00LL) { ok = false; break; }
+            if (D > 40000 * 8 || p.n_ent > 0x7fffff00LL) { ok = false; p.reason = 6; break; }
             cur.swap(nxt);
             level += 1;
         }
-        if (!ok || !ended || level < 2) return;
+        if (!ok || !ended || level < 2) { if (!p.reason) p.reason = 2; return; }
         const SubgroupInput& in = *s.in;
-        for (int v : in.pair_val) if (v >= s.R) return;  // reported by the level-synchronous path
+        for (int v : in.pair_val) if (v >= s.R) { p.reason = 7; return; }  // reported by the level-synchronous path
         p.n_levels = level;
         p.eligible = true;
     }
@@ -978,6 +981,13 @@ struct Engine
             scr(p.d_ops, sizeof(int2) * WALK_KMAX);
             scr(p.d_kid, sizeof(double) * WALK_KMAX);
             scr(p.d_paths, sizeof(int) * (size_t)WALK_SMAX * p.n_levels);
+        }
+        if (getenv("RAMBL_TRACE") && take.size() < n)
+        {
+            int why[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (const WalkPlan& p : plans) if (!p.eligible) why[std::min(std::max(p.reason, 0), 8)] += 1;
+            fprintf(stderr, "[rambl] device walk: %zu of %zu subgroups not eligible (reasons 1..8: %d %d %d %d %d %d %d %d)\n",
+                    n - take.size(), n, why[1], why[2], why[3], why[4], why[5], why[6], why[7], why[8]);
         }
         if (take.empty()) return 0;
         // ---- fill the static tables (pinned) on the workers, one copy to the device
@@ -1141,6 +1151,20 @@ struct Engine
             stats.d2h_bytes += (long long)(sizeof(int) * h_paths[k].size());
         }
         RAMBL_CUDA(cudaStreamSynchronize(st));
+        if (getenv("RAMBL_TRACE"))
+        {
+            long long sum_S = 0, glev = 0, unst = 0;
+            int max_S = 0, hist[WALK_NOT_RUN + 1] = {0};
+            for (const WalkResult& r : res)
+            {
+                sum_S += r.sum_S; glev += r.gibbs_levels; unst += r.unstaged_levels; max_S = std::max(max_S, r.max_S);
+                hist[std::min(std::max(r.status, 0), (int)WALK_NOT_RUN)] += 1;
+            }
+            fprintf(stderr, "[rambl] device walk: %lld Gibbs levels, mean %.1f strains, max %d, %lld levels unstaged; status counts:",
+                    glev, glev ? (double)sum_S / glev : 0.0, max_S, unst);
+            for (int k = 0; k <= WALK_NOT_RUN; ++k) fprintf(stderr, " %d", hist[k]);
+            fprintf(stderr, "\n");
+        }
         int taken = 0;
         std::vector<size_t> redo;
         for (size_t k = 0; k < take.size(); ++k)

@@ -4,7 +4,7 @@
 // (/root/reference/StrainCall/MultipleSequenceAlignment.hpp:87-107,
 //  MultipleSequenceAlignmentSP.cpp:10-301) as PartialOrderGraph::canonize_insert_at_level calls it
 // (PartialOrderGraph.cpp:449-455,507-519,546): every graph level whose insertions differ in length is
-// one PROBLEM; all problems of all subgroups go through one launch, one warp per problem.
+// one PROBLEM; all problems of all subgroups of a batch are solved together.
 //
 // The reference evaluates every DP cell with three loops over the s sequences already in the
 // profile and keeps one state per (cell, sequence).  Both collapse: (1) the per-sequence state of an
@@ -15,10 +15,22 @@
 // scores are integers (3,-5,-6,-2), so int32 is exact where the reference sums doubles, and the
 // reference's tie order (match >= insert >= delete) is kept.
 //
-// Layout: profile columns have a stable id (creation order); `ord` maps profile position -> id, so a
-// column insertion only shifts `ord`.  Letters live column-major in global scratch (colchar[id][row]);
-// rows above a column's birth row are '-' implicitly.  DP tables, class counts and `ord` sit in
-// shared memory; the wavefront runs one anti-diagonal per step across the lanes of the warp.
+// Mapping.  Real insertion levels are SMALL (a handful of letters against a profile of a dozen columns, tens to
+// hundreds of strings), so a warp per problem leaves most lanes idle and one oversized problem used to size the
+// shared memory of every CTA.  Problems are therefore dealt into SIZE CLASSES by their longest string; a class
+// gives each problem a group of G lanes (8, 16 or 32) of a CTA and a shared-memory region sized for
+// the class, so a CTA of the smallest class solves 16 problems at once.  Within a group:
+//   * profile columns have a stable id (creation order); `ord` maps profile position -> id, so a column
+//     insertion only shifts `ord`; letters live column-major in global scratch (colchar[id][row]);
+//   * the per-column sums against every letter class (what a DP cell needs) are kept INCREMENTALLY: aligning a
+//     string adds one letter or one gap to every column -- 7 additions -- instead of a 7x7 recomputation;
+//   * borders: the first row is a closed form, the first column a prefix sum over the group's lanes;
+//   * the interior runs as an anti-diagonal wavefront over the group's lanes;
+//   * the traceback is a short serial walk by one lane, but the profile update it implies is done by all lanes
+//     (prefix counts over the operation string give every operation its column and its letter).
+// A problem whose profile outgrows its class (more columns than the class holds) reports it and is solved again
+// in the next class; the last class keeps its tables in global memory and takes anything (no compiled-in limit
+// on columns or letters: the reference allocates its tables on the heap).
 #include "msa_sp.hpp"
 
 #include <algorithm>
@@ -61,29 +73,68 @@ __device__ __forceinline__ int classify(char ch)
 
 struct MsaArgs
 {
+    const int* prob;            // [n] problems of this launch (indices into the batch)
+    int n;
     const int* prob_seq_off;
     const int* seq_off;
     const char* chars;
-    const long long* colchar_off;
+    const long long* colchar_off;  // per launch slot
     char* colchar;
-    const long long* rows_off;
+    const long long* rows_off;     // per launch slot; row stride = WM
     char* rows;
-    const int* cap;
-    int* width;
-    int* status;
-    unsigned long long* cells;
-    int smem_W;  // largest cap in the batch
-    int smem_L;  // longest sequence in the batch
+    int* width;                 // per launch slot
+    int* status;                // per launch slot: 0 ok, 1 the profile outgrew the class
+    unsigned long long* cells;  // per launch slot
+    int WM, LM;                 // columns / letters the class holds
+    size_t region;              // bytes of one problem's tables
+    unsigned char* gtables;     // tables of the global-memory class (region bytes per slot), else null
 };
 
-__global__ void __launch_bounds__(32) msa_sp_kernel(MsaArgs a)
+__host__ __device__ inline size_t msa_region_bytes(int WM, int LM)
+{
+    size_t b = 0;
+    b += sizeof(int) * (size_t)(WM + 1) * (LM + 1);   // SC
+    b += sizeof(int) * (size_t)WM * 8 * 2;            // cnt, cs
+    b += sizeof(unsigned short) * (size_t)WM * 3;     // ord0, ord1, birth
+    b += (size_t)(WM + 1) * (LM + 1);                 // BT
+    b += (size_t)WM;                                  // firstgap
+    b += (size_t)(WM + LM + 2);                       // ops
+    b += (size_t)LM;                                  // seqcls
+    b += 16;                                          // W, ncol, err, k
+    return (b + 15) & ~(size_t)15;
+}
+
+template <int G>
+__device__ __forceinline__ int group_scan_incl(int x, int gl, unsigned gmask)
+{
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1)
+    {
+        const int y = __shfl_up_sync(gmask, x, o, G);
+        if (gl >= o) x += y;
+    }
+    return x;
+}
+
+// G lanes per problem, GROUPS problems per CTA; tables in shared memory, or in global memory when a.gtables
+template <int G, int GROUPS>
+__global__ void __launch_bounds__(G * GROUPS) msa_sp_kernel(MsaArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int p = blockIdx.x, lane = threadIdx.x;
-    const int WM = a.smem_W, LM = a.smem_L;
-    int* SC = reinterpret_cast<int*>(smem_raw);                // (WM+1) x (LM+1)
-    int* cnt = SC + (WM + 1) * (LM + 1);                       // WM x 8   (class counts per column id)
-    int* cs = cnt + WM * 8;                                    // WM x 8   (non-gap rows vs letter class)
+    __shared__ int sS[NCLS][8];
+    const int tid = threadIdx.x, gl = tid % G, grp = tid / G;
+    const int lane = tid & 31;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - gl));
+    for (int q = tid; q < NCLS * NCLS; q += G * GROUPS) sS[q / NCLS][q % NCLS] = c_S[q / NCLS][q % NCLS];
+    __syncthreads();
+    const int slot = blockIdx.x * GROUPS + grp;
+    if (slot >= a.n) return;  // whole groups leave together; no CTA barrier below
+    const int p = a.prob[slot];
+    const int WM = a.WM, LM = a.LM;
+    unsigned char* base = a.gtables ? a.gtables + (size_t)slot * a.region : smem_raw + (size_t)grp * a.region;
+    int* SC = reinterpret_cast<int*>(base);                    // (WM+1) x (LM+1)
+    int* cnt = SC + (WM + 1) * (LM + 1);                       // WM x 8   class counts per column id
+    int* cs = cnt + WM * 8;                                    // WM x 8   non-gap rows vs letter class
     unsigned short* ord0 = reinterpret_cast<unsigned short*>(cs + WM * 8);
     unsigned short* ord1 = ord0 + WM;
     unsigned short* birth = ord1 + WM;
@@ -91,80 +142,76 @@ __global__ void __launch_bounds__(32) msa_sp_kernel(MsaArgs a)
     unsigned char* firstgap = BT + (WM + 1) * (LM + 1);
     unsigned char* ops = firstgap + WM;                        // WM + LM + 2
     unsigned char* seqcls = ops + (WM + LM + 2);               // LM
-    __shared__ int sh_W, sh_ncol, sh_err;
+    int* sv = reinterpret_cast<int*>(base + a.region - 16);    // [0] W, [1] ncol, [2] err, [3] k
 
     const int s0 = a.prob_seq_off[p], s1 = a.prob_seq_off[p + 1];
     const int nrow = s1 - s0;
-    const int cap = a.cap[p];
-    char* colchar = a.colchar + a.colchar_off[p];
-    char* rows = a.rows + a.rows_off[p];
+    char* colchar = a.colchar + a.colchar_off[slot];
+    char* rows = a.rows + a.rows_off[slot];
     unsigned long long cells = 0;
 
     // ---- first sequence: one column per letter
     {
         const int b = a.seq_off[s0], len = a.seq_off[s0 + 1] - b;
-        if (lane == 0) { sh_err = (len > cap) ? 1 : 0; sh_W = len; sh_ncol = len; }
-        __syncwarp();
-        if (!sh_err)
-            for (int w = lane; w < len; w += 32)
+        if (gl == 0) { sv[2] = (len > WM) ? 1 : 0; sv[0] = len; sv[1] = len; }
+        __syncwarp(gmask);
+        if (!sv[2])
+            for (int w = gl; w < len; w += G)
             {
                 const char ch = a.chars[b + w];
-                for (int c = 0; c < 8; ++c) cnt[w * 8 + c] = 0;
-                cnt[w * 8 + classify(ch)] = 1;
+                const int cl = classify(ch);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { cnt[w * 8 + c] = 0; cs[w * 8 + c] = (cl != CLS_GAP && c < NCLS) ? sS[cl][c] : 0; }
+                cnt[w * 8 + cl] = 1;
                 ord0[w] = (unsigned short)w;
                 birth[w] = 0;
                 firstgap[w] = (ch == '-');
                 colchar[(long long)w * nrow] = ch;
             }
-        __syncwarp();
+        __syncwarp(gmask);
     }
     unsigned short* ord = ord0;
     unsigned short* ordn = ord1;
+    const int S0P = sS[0][CLS_PLUS], S0G = sS[0][CLS_GAP];
 
-    for (int t = 1; t < nrow && !sh_err; ++t)
+    for (int t = 1; t < nrow && !sv[2]; ++t)
     {
         const int b = a.seq_off[s0 + t], len = a.seq_off[s0 + t + 1] - b;
-        const int W = sh_W, m = W + 1, n = len + 1, s = t;
-        for (int j = lane; j < len; j += 32) seqcls[j] = (unsigned char)classify(a.chars[b + j]);
-        // per-column sums of the non-gap rows against every letter class
-        for (int k = lane; k < W * NCLS; k += 32)
+        const int W = sv[0], m = W + 1, n = len + 1, s = t;
+        for (int j = gl; j < len; j += G) seqcls[j] = (unsigned char)classify(a.chars[b + j]);
+        // ---- borders (MultipleSequenceAlignmentSP.cpp:65-137): the first row in closed form ...
+        for (int j = gl; j < n; j += G)
         {
-            const int col = ord[k / NCLS], y = k % NCLS;
-            int v = 0;
-#pragma unroll
-            for (int c = 0; c < NCLS; ++c)
-                if (c != CLS_GAP) v += cnt[col * 8 + c] * c_S[c][y];
-            cs[col * 8 + y] = v;
+            SC[j] = (j == 0) ? 0 : s * (S0P + (j - 1) * S0G);
+            BT[j] = (j == 0) ? (P_MAT | (P_MAT << 2)) : (P_INS | (P_INS << 2));
         }
-        __syncwarp();
-        // borders (MultipleSequenceAlignmentSP.cpp:65-137)
-        if (lane == 0)
+        // ... the first column as a running sum over the profile, G columns at a time
         {
-            SC[0] = 0;
-            BT[0] = P_MAT | (P_MAT << 2);
-            for (int j = 1; j < n; ++j)
+            int carry = 0;
+            for (int i0 = 1; i0 < m; i0 += G)
             {
-                SC[j] = SC[j - 1] + s * c_S[0][j == 1 ? CLS_PLUS : CLS_GAP];
-                BT[j] = P_INS | (P_INS << 2);
+                const int i = i0 + gl;
+                int v = 0;
+                if (i < m)
+                {
+                    const int col = ord[i - 1];
+                    v = cs[col * 8 + ((i == 1) ? CLS_PLUS : CLS_GAP)] + cnt[col * 8 + CLS_GAP] * 3;
+                }
+                const int x = group_scan_incl<G>(v, gl, gmask);
+                if (i < m)
+                {
+                    SC[i * n] = carry + x;
+                    BT[i * n] = P_DEL | (P_MAT << 2);  // per-row states here are never "ins" and never asked for "del"
+                }
+                carry += __shfl_sync(gmask, x, G - 1, G);
             }
         }
-        else if (lane == 1)
-        {
-            int acc = 0;
-            for (int i = 1; i < m; ++i)
-            {
-                const int col = ord[i - 1], y = (i == 1) ? CLS_PLUS : CLS_GAP;
-                acc += cs[col * 8 + y] + cnt[col * 8 + CLS_GAP] * 3;
-                SC[i * n] = acc;
-                BT[i * n] = P_DEL | (P_MAT << 2);  // per-row states here are never "ins" and never asked for "del"
-            }
-        }
-        __syncwarp();
-        // anti-diagonal wavefront over the interior (MultipleSequenceAlignmentSP.cpp:139-248)
+        __syncwarp(gmask);
+        // ---- anti-diagonal wavefront over the interior (MultipleSequenceAlignmentSP.cpp:139-248)
         for (int d = 2; d <= (m - 1) + (n - 1); ++d)
         {
             const int ilo = max(1, d - (n - 1)), ihi = min(m - 1, d - 1);
-            for (int i = ilo + lane; i <= ihi; i += 32)
+            for (int i = ilo + gl; i <= ihi; i += G)
             {
                 const int j = d - i;
                 const int cj = seqcls[j - 1];
@@ -173,8 +220,8 @@ __global__ void __launch_bounds__(32) msa_sp_kernel(MsaArgs a)
                 const int st_d = BT[(i - 1) * n + (j - 1)] >> 2;
                 const int st_l = BT[i * n + (j - 1)] >> 2;
                 const int st_u = BT[(i - 1) * n + j] >> 2;
-                const int r1 = SC[(i - 1) * n + (j - 1)] + cs[col * 8 + cj] + ngap * c_S[st_d == P_INS ? CLS_GAP : CLS_PLUS][cj];
-                const int r2 = SC[i * n + (j - 1)] + s * c_S[st_l == P_INS ? CLS_GAP : CLS_PLUS][cj];
+                const int r1 = SC[(i - 1) * n + (j - 1)] + cs[col * 8 + cj] + ngap * sS[st_d == P_INS ? CLS_GAP : CLS_PLUS][cj];
+                const int r2 = SC[i * n + (j - 1)] + s * sS[st_l == P_INS ? CLS_GAP : CLS_PLUS][cj];
                 const int r3 = SC[(i - 1) * n + j] + cs[col * 8 + (st_u == P_DEL ? CLS_GAP : CLS_PLUS)] + ngap * 3;
                 const int fg = firstgap[col];
                 int best, bt;
@@ -184,11 +231,11 @@ __global__ void __launch_bounds__(32) msa_sp_kernel(MsaArgs a)
                 SC[i * n + j] = best;
                 BT[i * n + j] = (unsigned char)bt;
             }
-            __syncwarp();
+            __syncwarp(gmask);
         }
         cells += (unsigned long long)(m - 1) * (n - 1);
-        // traceback and profile update (MultipleSequenceAlignmentSP.cpp:252-301)
-        if (lane == 0)
+        // ---- traceback (MultipleSequenceAlignmentSP.cpp:252-301): a serial walk, last operation first
+        if (gl == 0)
         {
             int x = m - 1, y = n - 1, k = 0;
             while (x != 0 || y != 0)
@@ -199,76 +246,100 @@ __global__ void __launch_bounds__(32) msa_sp_kernel(MsaArgs a)
                 else if (dir == P_INS) --y;
                 else --x;
             }
-            int po = 0, pn = 0, j = 0, ncol = sh_ncol, err = 0;
-            for (int q = k - 1; q >= 0; --q)
-            {
-                const int dir = ops[q];
-                int col;
-                char ch;
-                if (dir == P_INS)
-                {
-                    if (ncol >= cap) { err = 1; break; }
-                    col = ncol++;
-                    ch = a.chars[b + j++];
-                    for (int c = 0; c < 8; ++c) cnt[col * 8 + c] = 0;
-                    cnt[col * 8 + CLS_GAP] = t;
-                    cnt[col * 8 + classify(ch)] += 1;
-                    birth[col] = (unsigned short)t;
-                    firstgap[col] = 1;
-                }
-                else if (dir == P_MAT)
-                {
-                    col = ord[po++];
-                    ch = a.chars[b + j++];
-                    cnt[col * 8 + classify(ch)] += 1;
-                }
-                else
-                {
-                    col = ord[po++];
-                    ch = '-';
-                    cnt[col * 8 + CLS_GAP] += 1;
-                }
-                colchar[(long long)col * nrow + t] = ch;
-                ordn[pn++] = (unsigned short)col;
-            }
-            sh_W = pn;
-            sh_ncol = ncol;
-            if (err) sh_err = 1;
+            sv[3] = k;
         }
-        __syncwarp();
+        __syncwarp(gmask);
+        // ---- profile update by all lanes: operation f (in forward order) consumes profile position
+        // #(non-insert ops before f) and letter #(non-delete ops before f); an insert opens column ncol + #(inserts before f)
+        {
+            const int k = sv[3], ncol = sv[1];
+            int c_po = 0, c_j = 0, c_ins = 0, err = 0;
+            for (int f0 = 0; f0 < k; f0 += G)
+            {
+                const int f = f0 + gl;
+                const int dir = f < k ? ops[k - 1 - f] : -1;
+                const int is_ins = dir == P_INS ? 1 : 0, is_del = dir == P_DEL ? 1 : 0, in = f < k ? 1 : 0;
+                const int x_po = group_scan_incl<G>(in - is_ins, gl, gmask);
+                const int x_j = group_scan_incl<G>(in - is_del, gl, gmask);
+                const int x_ins = group_scan_incl<G>(is_ins, gl, gmask);
+                if (in)
+                {
+                    const int po = c_po + x_po - (in - is_ins), j = c_j + x_j - (in - is_del);
+                    int col;
+                    char ch;
+                    if (is_ins)
+                    {
+                        col = ncol + c_ins + x_ins - 1;
+                        if (col >= WM) err = 1;
+                        else
+                        {
+                            ch = a.chars[b + j];
+                            const int cl = classify(ch);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) { cnt[col * 8 + c] = 0; cs[col * 8 + c] = (cl != CLS_GAP && c < NCLS) ? sS[cl][c] : 0; }
+                            cnt[col * 8 + CLS_GAP] = t;
+                            cnt[col * 8 + cl] += 1;
+                            birth[col] = (unsigned short)t;
+                            firstgap[col] = 1;
+                        }
+                    }
+                    else if (!is_del)
+                    {
+                        col = ord[po];
+                        ch = a.chars[b + j];
+                        const int cl = classify(ch);
+                        cnt[col * 8 + cl] += 1;
+                        if (cl != CLS_GAP)
+                        {
+#pragma unroll
+                            for (int c = 0; c < NCLS; ++c) cs[col * 8 + c] += sS[cl][c];
+                        }
+                    }
+                    else
+                    {
+                        col = ord[po];
+                        ch = '-';
+                        cnt[col * 8 + CLS_GAP] += 1;
+                    }
+                    if (!err)
+                    {
+                        colchar[(long long)col * nrow + t] = ch;
+                        ordn[f] = (unsigned short)col;
+                    }
+                }
+                c_po += __shfl_sync(gmask, x_po, G - 1, G);
+                c_j += __shfl_sync(gmask, x_j, G - 1, G);
+                c_ins += __shfl_sync(gmask, x_ins, G - 1, G);
+            }
+            err = __any_sync(gmask, err) ? 1 : 0;
+            if (gl == 0)
+            {
+                sv[0] = k;
+                sv[1] = ncol + c_ins;
+                if (err) sv[2] = 1;
+            }
+        }
+        __syncwarp(gmask);
         unsigned short* tmp = ord; ord = ordn; ordn = tmp;
     }
-    __syncwarp();
+    __syncwarp(gmask);
     // ---- rows of the final profile (MSA::get, MultipleSequenceAlignment.hpp:56-66)
-    if (!sh_err)
+    if (!sv[2])
     {
-        const int W = sh_W;
-        for (int k = lane; k < nrow * W; k += 32)
+        const int W = sv[0];
+        for (int k = gl; k < nrow * W; k += G)
         {
             const int t = k / W, w = k % W;
             const int col = ord[w];
-            rows[(long long)t * cap + w] = (t >= birth[col]) ? colchar[(long long)col * nrow + t] : '-';
+            rows[(long long)t * WM + w] = (t >= birth[col]) ? colchar[(long long)col * nrow + t] : '-';
         }
     }
-    if (lane == 0)
+    if (gl == 0)
     {
-        a.width[p] = sh_W;
-        a.status[p] = sh_err;
-        a.cells[p] = cells;
+        a.width[slot] = sv[0];
+        a.status[slot] = sv[2];
+        a.cells[slot] = cells;
     }
-}
-
-size_t msa_smem_bytes(int WM, int LM)
-{
-    size_t b = 0;
-    b += sizeof(int) * (size_t)(WM + 1) * (LM + 1);
-    b += sizeof(int) * (size_t)WM * 8 * 2;
-    b += sizeof(unsigned short) * (size_t)WM * 3;
-    b += (size_t)(WM + 1) * (LM + 1);
-    b += (size_t)WM;
-    b += (size_t)(WM + LM + 2);
-    b += (size_t)LM;
-    return (b + 15) & ~(size_t)15;
 }
 
 bool g_score_ready = false;
@@ -279,6 +350,24 @@ void upload_scores()
     for (int x = 0; x < NCLS; ++x) for (int y = 0; y < NCLS; ++y) S[x][y] = host_score(x, y);
     RAMBL_CUDA(cudaMemcpyToSymbol(c_S, S, sizeof(S)));
     g_score_ready = true;
+}
+
+// size classes: a problem starts in the first class that holds its longest string
+struct MsaClass { int LM, WM, G; };
+const MsaClass kClasses[] = {{8, 16, 8}, {16, 32, 8}, {32, 64, 16}, {63, 255, 32}};
+constexpr int kNumClasses = 4;  // + the global-memory class, index kNumClasses
+
+template <int G, int GROUPS>
+void launch_class(const MsaArgs& a, cudaStream_t st)
+{
+    const size_t smem = a.gtables ? 16 : a.region * (size_t)GROUPS;
+    static size_t configured = 0;
+    if (smem > configured)
+    {
+        RAMBL_CUDA(cudaFuncSetAttribute(msa_sp_kernel<G, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    msa_sp_kernel<G, GROUPS><<<(a.n + GROUPS - 1) / GROUPS, G * GROUPS, smem, st>>>(a);
 }
 
 }  // namespace
@@ -301,83 +390,132 @@ void msa_sp_align_batch(const MsaBatch& in, MsaResult& out, cudaStream_t stream)
     out.rows.clear();
     out.dp_cells = 0;
     out.kernel_ms = 0;
+    out.launches = 0;
     if (P <= 0) return;
     require_device();
     upload_scores();
 
-    std::vector<long long> colchar_off(P + 1, 0), rows_off(P + 1, 0);
-    int WM = 1, LM = 1;
+    // ---- per problem: longest string, letters in total -> starting class
+    std::vector<int> lmax(P, 1), cls(P, 0);
+    std::vector<long long> letters(P, 0);
+    std::vector<std::vector<int>> todo(kNumClasses + 1);
     for (int p = 0; p < P; ++p)
     {
         const int s0 = in.prob_seq_off[p], s1 = in.prob_seq_off[p + 1];
         if (s1 <= s0) throw Error(RAMBL_ERR_INVALID, "msa problem without sequences");
-        long long total = 0;
+        if (s1 - s0 > 65535) throw Error(RAMBL_ERR_CAPACITY, "an insertion level with more than 65535 strings");
         for (int s = s0; s < s1; ++s)
         {
             const int len = in.seq_off[s + 1] - in.seq_off[s];
-            if (len > MSA_LMAX) throw Error(RAMBL_ERR_CAPACITY, "insertion longer than MSA_LMAX letters");
-            LM = std::max(LM, len);
-            total += len;
+            lmax[p] = std::max(lmax[p], len);
+            letters[p] += len;
         }
-        const int cap = (int)std::min<long long>(std::max<long long>(total, 1), MSA_WMAX);
-        out.cap[p] = cap;
-        WM = std::max(WM, cap);
-        const long long nrow = s1 - s0;
-        colchar_off[p + 1] = colchar_off[p] + (long long)cap * nrow;
-        rows_off[p + 1] = rows_off[p] + (long long)cap * nrow;
+        int c = 0;
+        while (c < kNumClasses && lmax[p] > kClasses[c].LM) ++c;
+        cls[p] = c;
+        todo[c].push_back(p);
     }
-    for (int p = 0; p <= P; ++p) out.row_off[p] = rows_off[p];
-    const size_t smem = msa_smem_bytes(WM, LM);
-    if (smem > 200 * 1024) throw Error(RAMBL_ERR_CAPACITY, "msa problem does not fit shared memory");
 
     const size_t nseq = in.seq_off.size() - 1, nchar = in.chars.size();
-    DevBuf<int> d_pso, d_so, d_cap, d_width, d_status;
-    DevBuf<char> d_chars, d_colchar, d_rows;
-    DevBuf<long long> d_cco, d_ro;
-    DevBuf<unsigned long long> d_cells;
-    d_pso.reserve(P + 1); d_so.reserve(nseq + 1); d_cap.reserve(P); d_width.reserve(P); d_status.reserve(P);
-    d_chars.reserve(std::max<size_t>(nchar, 1)); d_colchar.reserve(std::max<long long>(colchar_off[P], 1));
-    d_rows.reserve(std::max<long long>(rows_off[P], 1)); d_cco.reserve(P + 1); d_ro.reserve(P + 1); d_cells.reserve(P);
+    DevBuf<int> d_pso, d_so;
+    DevBuf<char> d_chars;
+    d_pso.reserve(P + 1); d_so.reserve(nseq + 1); d_chars.reserve(std::max<size_t>(nchar, 1));
     RAMBL_CUDA(cudaMemcpyAsync(d_pso.p, in.prob_seq_off.data(), sizeof(int) * (P + 1), cudaMemcpyHostToDevice, stream));
     RAMBL_CUDA(cudaMemcpyAsync(d_so.p, in.seq_off.data(), sizeof(int) * (nseq + 1), cudaMemcpyHostToDevice, stream));
     if (nchar) RAMBL_CUDA(cudaMemcpyAsync(d_chars.p, in.chars.data(), nchar, cudaMemcpyHostToDevice, stream));
-    RAMBL_CUDA(cudaMemcpyAsync(d_cap.p, out.cap.data(), sizeof(int) * P, cudaMemcpyHostToDevice, stream));
-    RAMBL_CUDA(cudaMemcpyAsync(d_cco.p, colchar_off.data(), sizeof(long long) * (P + 1), cudaMemcpyHostToDevice, stream));
-    RAMBL_CUDA(cudaMemcpyAsync(d_ro.p, rows_off.data(), sizeof(long long) * (P + 1), cudaMemcpyHostToDevice, stream));
 
-    MsaArgs a;
-    a.prob_seq_off = d_pso.p; a.seq_off = d_so.p; a.chars = d_chars.p;
-    a.colchar_off = d_cco.p; a.colchar = d_colchar.p; a.rows_off = d_ro.p; a.rows = d_rows.p;
-    a.cap = d_cap.p; a.width = d_width.p; a.status = d_status.p; a.cells = d_cells.p;
-    a.smem_W = WM; a.smem_L = LM;
-    RAMBL_CUDA(cudaFuncSetAttribute(msa_sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    std::vector<std::vector<char>> prob_rows(P);  // rows of problem p, compact: row t at t * width[p]
+    DevBuf<int> d_prob, d_width, d_status;
+    DevBuf<long long> d_cco, d_ro;
+    DevBuf<unsigned long long> d_cells;
+    DevBuf<char> d_colchar, d_rows;
+    DevBuf<unsigned char> d_tables;
     cudaEvent_t e0, e1;
     RAMBL_CUDA(cudaEventCreate(&e0));
     RAMBL_CUDA(cudaEventCreate(&e1));
-    RAMBL_CUDA(cudaEventRecord(e0, stream));
-    msa_sp_kernel<<<P, 32, smem, stream>>>(a);
-    RAMBL_CUDA(cudaEventRecord(e1, stream));
-    RAMBL_CUDA(cudaGetLastError());
-
-    out.rows.resize((size_t)rows_off[P]);
-    std::vector<int> status(P);
-    std::vector<unsigned long long> cells(P);
-    RAMBL_CUDA(cudaMemcpyAsync(out.width.data(), d_width.p, sizeof(int) * P, cudaMemcpyDeviceToHost, stream));
-    RAMBL_CUDA(cudaMemcpyAsync(status.data(), d_status.p, sizeof(int) * P, cudaMemcpyDeviceToHost, stream));
-    RAMBL_CUDA(cudaMemcpyAsync(cells.data(), d_cells.p, sizeof(unsigned long long) * P, cudaMemcpyDeviceToHost, stream));
-    if (rows_off[P]) RAMBL_CUDA(cudaMemcpyAsync(&out.rows[0], d_rows.p, (size_t)rows_off[P], cudaMemcpyDeviceToHost, stream));
-    RAMBL_CUDA(cudaStreamSynchronize(stream));
-    float ms = 0;
-    RAMBL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    for (int c = 0; c <= kNumClasses; ++c)
+    {
+        std::vector<int>& list = todo[c];
+        if (list.empty()) continue;
+        std::sort(list.begin(), list.end());
+        const int n = (int)list.size();
+        const bool global = c == kNumClasses;
+        int WM, LM, G;
+        if (!global) { WM = kClasses[c].WM; LM = kClasses[c].LM; G = kClasses[c].G; }
+        else
+        {   // tables in global memory: sized for the widest profile any of these problems can reach
+            long long wm = 1;
+            LM = 1;
+            for (int p : list) { wm = std::max(wm, letters[p]); LM = std::max(LM, lmax[p]); }
+            if (wm > 65535) throw Error(RAMBL_ERR_CAPACITY, "an insertion level with more than 65535 letters");
+            WM = (int)wm;
+            G = 32;
+        }
+        const size_t region = msa_region_bytes(WM, LM);
+        std::vector<long long> cco(n + 1, 0), ro(n + 1, 0);
+        for (int k = 0; k < n; ++k)
+        {
+            const long long nrow = in.prob_seq_off[list[k] + 1] - in.prob_seq_off[list[k]];
+            cco[k + 1] = cco[k] + (long long)WM * nrow;
+            ro[k + 1] = ro[k] + (long long)WM * nrow;
+        }
+        d_prob.reserve(n); d_width.reserve(n); d_status.reserve(n); d_cells.reserve(n); d_cco.reserve(n + 1); d_ro.reserve(n + 1);
+        d_colchar.reserve(std::max<long long>(cco[n], 1));
+        d_rows.reserve(std::max<long long>(ro[n], 1));
+        if (global) d_tables.reserve(region * (size_t)n);
+        RAMBL_CUDA(cudaMemcpyAsync(d_prob.p, list.data(), sizeof(int) * n, cudaMemcpyHostToDevice, stream));
+        RAMBL_CUDA(cudaMemcpyAsync(d_cco.p, cco.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, stream));
+        RAMBL_CUDA(cudaMemcpyAsync(d_ro.p, ro.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, stream));
+        MsaArgs a;
+        a.prob = d_prob.p; a.n = n; a.prob_seq_off = d_pso.p; a.seq_off = d_so.p; a.chars = d_chars.p;
+        a.colchar_off = d_cco.p; a.colchar = d_colchar.p; a.rows_off = d_ro.p; a.rows = d_rows.p;
+        a.width = d_width.p; a.status = d_status.p; a.cells = d_cells.p;
+        a.WM = WM; a.LM = LM; a.region = region; a.gtables = global ? d_tables.p : nullptr;
+        RAMBL_CUDA(cudaEventRecord(e0, stream));
+        if (global) launch_class<32, 4>(a, stream);
+        else if (G == 8) launch_class<8, 16>(a, stream);
+        else if (G == 16) launch_class<16, 8>(a, stream);
+        else launch_class<32, 2>(a, stream);  // 100 KB of tables per problem: two per SM
+        RAMBL_CUDA(cudaEventRecord(e1, stream));
+        RAMBL_CUDA(cudaGetLastError());
+        out.launches += 1;
+        std::vector<int> width(n), status(n);
+        std::vector<unsigned long long> cells(n);
+        std::vector<char> rows((size_t)ro[n]);
+        RAMBL_CUDA(cudaMemcpyAsync(width.data(), d_width.p, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+        RAMBL_CUDA(cudaMemcpyAsync(status.data(), d_status.p, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+        RAMBL_CUDA(cudaMemcpyAsync(cells.data(), d_cells.p, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, stream));
+        if (ro[n]) RAMBL_CUDA(cudaMemcpyAsync(rows.data(), d_rows.p, (size_t)ro[n], cudaMemcpyDeviceToHost, stream));
+        RAMBL_CUDA(cudaStreamSynchronize(stream));
+        float ms = 0;
+        RAMBL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        out.kernel_ms += ms;
+        for (int k = 0; k < n; ++k)
+        {
+            const int p = list[k];
+            if (status[k])
+            {   // the profile outgrew the class: once more in the next one
+                if (global) throw Error(RAMBL_ERR_CAPACITY, "msa profile outgrew the global-memory tables");
+                todo[c + 1].push_back(p);
+                continue;
+            }
+            out.dp_cells += cells[k];
+            const int nrow = in.prob_seq_off[p + 1] - in.prob_seq_off[p], w = width[k];
+            out.width[p] = w;
+            out.cap[p] = std::max(w, 1);
+            prob_rows[p].resize((size_t)nrow * std::max(w, 1));
+            for (int t = 0; t < nrow; ++t)
+                memcpy(prob_rows[p].data() + (size_t)t * std::max(w, 1), rows.data() + ro[k] + (long long)t * WM, (size_t)w);
+        }
+    }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    out.kernel_ms = ms;
-    out.launches = 1;
+    long long total = 0;
+    for (int p = 0; p < P; ++p) { out.row_off[p] = total; total += (long long)prob_rows[p].size(); }
+    out.row_off[P] = total;
+    out.rows.resize((size_t)total);
     for (int p = 0; p < P; ++p)
-    {
-        if (status[p]) throw Error(RAMBL_ERR_CAPACITY, "msa profile grew past MSA_WMAX columns");
-        out.dp_cells += cells[p];
-    }
+        if (!prob_rows[p].empty()) memcpy(&out.rows[(size_t)out.row_off[p]], prob_rows[p].data(), prob_rows[p].size());
 }
 
 }  // namespace rambl

@@ -4,8 +4,8 @@
 
 namespace rambl {
 
-constexpr int MSA_WMAX = 255;  // profile columns per problem
-constexpr int MSA_LMAX = 63;   // letters per insertion
+// No compiled-in limit on columns or letters: problems are dealt into shared-memory size classes and anything
+// larger runs with its tables in global memory (msa_sp.cu).
 
 // CSR of problems -> sequences -> letters.  Sequences of a problem are aligned in the given order
 // (the caller sorts them the way PartialOrderGraph::canonize_insert_at_level does).

@@ -77,7 +77,7 @@ size_t walk_smem_bytes(int nb, int tile_S)
 namespace {
 
 template <int NB>
-__global__ void __launch_bounds__(32 * NB, 1) k_walk(const WalkSub* __restrict__ subs, WalkParams prm, int tile_S)
+__global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const WalkSub* __restrict__ subs, WalkParams prm, int tile_S)
 {
     constexpr int NS = 4;
     constexpr int NT = 32 * NB;
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(32 * NB, 1) k_walk(const WalkSub* __restrict__
     unsigned char* sp = walk_smem;
     GibbsShared gs;
     gs.wbuf = carve<double>(sp, 2 * (size_t)NB * tile_S * 32);
-    gs.tile_S = tile_S;
+    gs.wbuf_doubles = 2 * (size_t)NB * tile_S * 32;
     gs.masses = carve<double>(sp, (size_t)NB * WALK_SMAX);
     gs.mass0 = carve<double>(sp, WALK_SMAX);
     gs.row_S = WALK_SMAX;
@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(32 * NB, 1) k_walk(const WalkSub* __restrict__
 
     unsigned uses0 = 0, uses1 = 0;
     unsigned long long rounds = 0, passes = 0;
-    long long n_draws = 0, n_updates = 0, n_pairs = 0, n_gbytes = 0;  // thread 0 only
+    long long n_draws = 0, n_updates = 0, n_pairs = 0, n_gbytes = 0, sum_S = 0;  // thread 0 only
+    int n_glev = 0, n_unstaged = 0, max_S = 0;
 
     if (tid == 0)
     {
@@ -414,7 +415,11 @@ __global__ void __launch_bounds__(32 * NB, 1) k_walk(const WalkSub* __restrict__
                 // ---- np_bayes_clustering: the sequential Gibbs chain, NB blocks of 32 draws per round
                 for (int s = tid; s < S; s += NT) ab_io[s] = ws.ab[s];
                 __syncthreads();
-                gibbs_w_chain<NB, NS, false>(gs, uses0, uses1, S, D, nsweeps, true, wt, codes, prm.uniforms, ab_io, rounds, passes,
+                // as many 32-draw blocks per round as the level's tiles leave room for in the tile buffers; a level too wide
+                // for even one block reads its weights from L1/L2 with all NB blocks
+                int nb = (int)min((size_t)NB, gs.wbuf_doubles / (2 * (size_t)S * 32));
+                if (nb == 0) nb = NB;
+                gibbs_w_chain<NB, NS, false>(gs, uses0, uses1, nb, S, D, nsweeps, true, wt, codes, prm.uniforms, ab_io, rounds, passes,
                                              prm.counters);
                 if (warp == 0)
                 {   // normalise the masses; fold the averaged letter counts into the models (lines 217-243)
@@ -445,6 +450,10 @@ __global__ void __launch_bounds__(32 * NB, 1) k_walk(const WalkSub* __restrict__
                 {
                     n_draws += (long long)D * nsweeps;
                     n_gbytes += (long long)nsweeps * D * (S + 1) * 8;
+                    n_glev += 1;
+                    sum_S += S;
+                    max_S = max(max_S, S);
+                    if (2 * (size_t)S * 32 > gs.wbuf_doubles) n_unstaged += 1;
                 }
             }
             __syncthreads();
@@ -679,6 +688,7 @@ __global__ void __launch_bounds__(32 * NB, 1) k_walk(const WalkSub* __restrict__
         r.reason_level = level;
         r.draws = n_draws; r.loglik_updates = n_updates; r.weight_pairs = n_pairs; r.gibbs_bytes = n_gbytes;
         r.rounds = rounds; r.passes = passes;
+        r.sum_S = sum_S; r.gibbs_levels = n_glev; r.unstaged_levels = n_unstaged; r.max_S = max_S; r.pad = 0;
         *res = r;
         if (prm.counters)
         {

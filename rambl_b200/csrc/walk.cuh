@@ -48,6 +48,8 @@ struct WalkResult
     int status, n_cands, levels, reason_level;
     long long draws, loglik_updates, weight_pairs, gibbs_bytes;
     unsigned long long rounds, passes;
+    long long sum_S;                           // candidate strains summed over the Gibbs levels
+    int gibbs_levels, unstaged_levels, max_S, pad;
 };
 
 struct WalkSub

@@ -77,10 +77,22 @@ def test_msa_kernel_properties_at_scale():
         assert rows[k] == refpy.msa_align(probs[k], "oracle")
 
 
-def test_msa_capacity_is_a_loud_error():
-    with pytest.raises(api.RamblError) as ei:
-        api.msa_align_batch([["A" * 100, "C" * 3]])
-    assert ei.value.code == api.RAMBL_ERR_CAPACITY
+def test_msa_size_classes_and_oversize_problems():
+    """Problems are dealt into shared-memory size classes by their longest string; a profile that outgrows its class
+    moves up, and anything beyond the largest class runs with its tables in global memory -- no compiled-in limit
+    (the reference allocates on the heap).  Every class boundary and the oversize path, against the oracle."""
+    rnd = np.random.default_rng(9)
+    probs = [["A" * 100, "C" * 3], ["ACGT" * 40, "TTGA" * 30, "G" * 70, "AC"], ["A" * 64, "A" * 63, "C"]]
+    for lm in (8, 9, 16, 17, 32, 33, 63, 64):
+        for n in (2, 5, 40):
+            seqs = ["".join(rnd.choice(list("ACGT"), size=int(rnd.integers(1, lm + 1)))) for _ in range(n)]
+            seqs[0] = "".join(rnd.choice(list("ACGT"), size=lm))
+            probs.append(sorted(seqs, key=lambda x: -len(x)))
+    # many distinct short strings: the profile grows past the 16 columns of the smallest class
+    probs.append(sorted(["".join(rnd.choice(list("ACGT"), size=int(rnd.integers(1, 9)))) for _ in range(60)], key=lambda x: -len(x)))
+    rows, st = api.msa_align_batch(probs)
+    for p, r in zip(probs, rows):
+        assert r == refpy.msa_align(p, "oracle"), p
 
 
 # ---- whole hot path ------------------------------------------------------------------------------
