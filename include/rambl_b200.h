@@ -102,6 +102,14 @@ int rambl_batch_add_subgroup(rambl_batch* b, const char* gene, int32_t n_reads, 
                              const char* const* cigar, const char* const* seq, const int32_t* copies,
                              const int32_t* pair_off, const int32_t* pair_val);
 
+/* The same with the CIGAR and read strings packed: read i has CIGAR cigar_chars[cigar_off[i] .. cigar_off[i+1]) and
+ * letters seq_chars[seq_off[i] .. seq_off[i+1]) (no terminators) -- for hosts that keep their reads in arenas (and for
+ * bindings where an array of C strings is expensive to build). */
+int rambl_batch_add_subgroup_packed(rambl_batch* b, const char* gene, int32_t n_reads, const int32_t* pos,
+                                    const int64_t* cigar_off, const char* cigar_chars, const int64_t* seq_off,
+                                    const char* seq_chars, const int32_t* copies, const int32_t* pair_off,
+                                    const int32_t* pair_val);
+
 /* A subgroup whose graph was built elsewhere (e.g. by the reference's own PartialOrderGraph): the `nodes`
  * vector flattened in order.  Node u has AlignState state[u] (mat=0, mis, ins, del; PartialOrderGraph.hpp:82),
  * label label_chars[label_off[u]..label_off[u+1]), ordered successors out_to[out_off[u]..out_off[u+1]) and an

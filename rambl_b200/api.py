@@ -66,6 +66,8 @@ SYMBOLS = {
     "rambl_batch_create": (C.c_void_p, []),
     "rambl_batch_destroy": (None, [C.c_void_p]),
     "rambl_batch_add_subgroup": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, _i32p, _strp, _strp, _i32p, _i32p, _i32p]),
+    "rambl_batch_add_subgroup_packed": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, _i32p, _i64p, C.c_char_p, _i64p, C.c_char_p,
+                                                  _i32p, _i32p, _i32p]),
     "rambl_batch_add_graph": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint8), _i32p, C.c_char_p, _i32p, _i32p,
                                         _i32p, _i32p, _i32p, _i32p, C.c_char_p, _i32p, _i32p, _i32p]),
     "rambl_batch_build_graphs": (C.c_int, [C.c_void_p]),
@@ -257,9 +259,28 @@ class StrainCallBatch:
         self._nreads.append(len(rc_))
         return rc
 
+    def add_subgroup_packed(self, gene: str, pos, cigar_off, cigar_chars: bytes, seq_off, seq_chars: bytes, copies,
+                            pair_off=None, pair_val=None) -> int:
+        """add_subgroup with the CIGAR and read strings as two byte arenas + offsets (no per-read objects)."""
+        p, c = _i32(pos), _i32(copies)
+        co = np.ascontiguousarray(cigar_off, dtype=np.int64)
+        so = np.ascontiguousarray(seq_off, dtype=np.int64)
+        po = _i32(pair_off) if pair_off is not None else None
+        pv = _i32(pair_val) if pair_val is not None else None
+        rc = lib().rambl_batch_add_subgroup_packed(
+            self._h, gene.encode(), len(p), p.ctypes.data_as(_i32p), co.ctypes.data_as(_i64p), cigar_chars,
+            so.ctypes.data_as(_i64p), seq_chars, c.ctypes.data_as(_i32p),
+            po.ctypes.data_as(_i32p) if po is not None else None, pv.ctypes.data_as(_i32p) if pv is not None else None)
+        if rc < 0:
+            _check(-rc)
+        self._nreads.append(len(p))
+        return rc
+
     def add(self, sg) -> int:
-        """Add a rambl_b200.synth.Subgroup."""
-        return self.add_subgroup(sg.gene, sg.pos, sg.cigar, sg.seq, sg.cn, sg.pair_off, sg.pair_val)
+        """Add a rambl_b200.synth.Subgroup (through its packed host buffers, built once per subgroup)."""
+        pk = sg.packed()
+        return self.add_subgroup_packed(sg.gene, pk["pos"], pk["cigar_off"], pk["cigar_chars"], pk["seq_off"], pk["seq_chars"],
+                                        pk["cn"], sg.pair_off, sg.pair_val)
 
     def build_graphs(self):
         _check(lib().rambl_batch_build_graphs(self._h))

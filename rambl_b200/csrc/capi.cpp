@@ -328,6 +328,47 @@ int rambl_batch_add_subgroup(rambl_batch* b, const char* gene, int32_t n_reads, 
     return rc == RAMBL_OK ? index : -rc;
 }
 
+int rambl_batch_add_subgroup_packed(rambl_batch* b, const char* gene, int32_t n_reads, const int32_t* pos,
+                                    const int64_t* cigar_off, const char* cigar_chars, const int64_t* seq_off,
+                                    const char* seq_chars, const int32_t* copies, const int32_t* pair_off,
+                                    const int32_t* pair_val)
+{
+    int index = -1;
+    int rc = guarded([&] {
+        if (!b || !gene || n_reads < 0 || (n_reads > 0 && (!pos || !cigar_off || !cigar_chars || !seq_off || !seq_chars || !copies)))
+            throw Error(RAMBL_ERR_INVALID, "null argument");
+        std::unique_ptr<Subgroup> s(new Subgroup);
+        s->gene = gene;
+        s->reads.reserve(n_reads);
+        s->input.read_cn.reserve(n_reads);
+        for (int i = 0; i < n_reads; ++i)
+        {
+            if (copies[i] < 1) throw Error(RAMBL_ERR_INVALID, "copy number must be >= 1");
+            if (cigar_off[i + 1] < cigar_off[i] || seq_off[i + 1] < seq_off[i]) throw Error(RAMBL_ERR_INVALID, "string offsets must not decrease");
+            s->reads.push_back({pos[i], std::string(cigar_chars + cigar_off[i], cigar_chars + cigar_off[i + 1]),
+                                std::string(seq_chars + seq_off[i], seq_chars + seq_off[i + 1]), copies[i]});
+            s->input.read_cn.push_back(copies[i]);
+        }
+        if (pair_off && pair_val)
+        {
+            s->input.pair_off.assign(pair_off, pair_off + n_reads + 1);
+            s->input.pair_val.assign(pair_val, pair_val + pair_off[n_reads]);
+        }
+        else
+        {
+            s->input.pair_off.assign(1, 0);
+            for (int i = 0; i < n_reads; ++i)
+            {
+                s->input.pair_val.insert(s->input.pair_val.end(), copies[i], -1);
+                s->input.pair_off.push_back((int)s->input.pair_val.size());
+            }
+        }
+        b->subs.push_back(std::move(s));
+        index = (int)b->subs.size() - 1;
+    });
+    return rc == RAMBL_OK ? index : -rc;
+}
+
 int rambl_batch_add_graph(rambl_batch* b, int32_t n_nodes, int32_t n_reads, const uint8_t* state,
                           const int32_t* label_off, const char* label_chars, const int32_t* out_off,
                           const int32_t* out_to, const int32_t* pool_off, const int32_t* pool_rid,

@@ -850,12 +850,13 @@ struct Engine
         bool multi = false;                  // some read-pool entry has more than one letter
         std::vector<int> order;              // nodes in walk order (levels concatenated)
         std::vector<int> lvl_ent_off;        // [n_levels + 1]
+        std::vector<unsigned char> lvl_dup;  // [n_levels] a read with several entries on the level
         long long n_ent = 0, n_chars = 0;
         // offsets into the static arena (bytes) and the scratch arena (bytes)
-        size_t o_label_off = 0, o_out_off = 0, o_out_to = 0, o_out_cover = 0, o_lvl = 0, o_rid = 0, o_cn = 0, o_soff = 0,
+        size_t o_label_off = 0, o_out_off = 0, o_out_to = 0, o_out_cover = 0, o_lvl = 0, o_dup = 0, o_rid = 0, o_cn = 0, o_soff = 0,
                o_len = 0, o_chars = 0, o_pair_off = 0, o_pair_val = 0;
         size_t d_present = 0, d_free = 0, d_cand0 = 0, d_cand1 = 0, d_trail = 0, d_W = 0, d_doff = 0, d_dent = 0, d_dmate = 0,
-               d_fresh = 0, d_ab = 0, d_ops = 0, d_kid = 0, d_res = 0, d_paths = 0, d_fslot = 0, d_fab = 0;
+               d_fresh = 0, d_ab = 0, d_ops = 0, d_kid = 0, d_lut = 0, d_res = 0, d_paths = 0, d_fslot = 0, d_fab = 0;
         int trail_cap = 0;
     };
     std::vector<WalkPlan> plans;
@@ -887,6 +888,7 @@ struct Engine
         {
             if (ended) { ok = false; p.reason = 2; break; }  // something follows "$"
             long long m = 0, D = 0;
+            unsigned char dup = 0;
             nxt.clear();
             for (int u : cur)
             {
@@ -897,8 +899,8 @@ struct Engine
                     for (int e = g.pool_off[u]; e < g.pool_off[u + 1]; ++e)
                     {
                         const int rid = g.pool_rid[e], cn = g.pool_cn[e], len = g.pool_str_off[e + 1] - g.pool_str_off[e];
-                        if (seen_rid[rid] == level) { ok = false; p.reason = 3; break; }
                         if (cn < 1 || cn > 255 || len < 1 || len > 255) { ok = false; p.reason = 4; break; }
+                        if (seen_rid[rid] == level) dup = 1;  // its further entries are added after the first, in entry order
                         seen_rid[rid] = level;
                         if (len > 1) p.multi = true;
                         m += 1; D += cn; p.n_chars += len;
@@ -917,6 +919,7 @@ struct Engine
             for (int v : nxt) level_of[v] = -1;
             p.n_ent += m;
             p.lvl_ent_off.push_back((int)p.n_ent);
+            p.lvl_dup.push_back(dup);
             p.max_m = std::max<long long>(p.max_m, m);
             p.max_D = std::max<long long>(p.max_D, D);
             if (D > 40000 * 8 || p.n_ent > 0x7fffff00LL) { ok = false; p.reason = 6; break; }
@@ -958,6 +961,7 @@ struct Engine
             put(p.o_out_to, sizeof(int) * g.out_to.size());
             put(p.o_out_cover, sizeof(int) * g.out_to.size());
             put(p.o_lvl, sizeof(int) * p.lvl_ent_off.size());
+            put(p.o_dup, p.lvl_dup.size());
             put(p.o_rid, sizeof(unsigned) * p.n_ent);
             put(p.o_cn, (size_t)p.n_ent);
             if (p.multi) { put(p.o_soff, sizeof(unsigned) * p.n_ent); put(p.o_len, (size_t)p.n_ent); }
@@ -980,6 +984,7 @@ struct Engine
             scr(p.d_ab, sizeof(double) * WALK_SMAX);
             scr(p.d_ops, sizeof(int2) * WALK_KMAX);
             scr(p.d_kid, sizeof(double) * WALK_KMAX);
+            scr(p.d_lut, sizeof(double) * WALK_SMAX * 36);
             scr(p.d_paths, sizeof(int) * (size_t)WALK_SMAX * p.n_levels);
         }
         if (getenv("RAMBL_TRACE") && take.size() < n)
@@ -1012,18 +1017,24 @@ struct Engine
                 memcpy(H + p.o_out_cover, g.out_cover.data(), sizeof(int) * g.out_to.size());
             }
             memcpy(H + p.o_lvl, p.lvl_ent_off.data(), sizeof(int) * p.lvl_ent_off.size());
+            memcpy(H + p.o_dup, p.lvl_dup.data(), p.lvl_dup.size());
             unsigned* rid = reinterpret_cast<unsigned*>(H + p.o_rid);
             unsigned char* cn = reinterpret_cast<unsigned char*>(H + p.o_cn);
             unsigned* soff = p.multi ? reinterpret_cast<unsigned*>(H + p.o_soff) : nullptr;
             unsigned char* len = p.multi ? reinterpret_cast<unsigned char*>(H + p.o_len) : nullptr;
             char* chars = H + p.o_chars;
             size_t at = 0, at_c = 0;
+            std::vector<int> seen(std::max(1, g.n_reads), -1);
+            size_t lvl = 0;
             for (int u : p.order)
             {
                 if (u == 0 || u == g.end_node) continue;
                 for (int e = g.pool_off[u]; e < g.pool_off[u + 1]; ++e, ++at)
                 {
-                    rid[at] = (unsigned)g.pool_rid[e];
+                    while (lvl + 1 < p.lvl_ent_off.size() && (long long)at >= p.lvl_ent_off[lvl + 1]) ++lvl;
+                    const int r0 = g.pool_rid[e];
+                    rid[at] = (unsigned)r0 | (seen[r0] == (int)lvl ? 0x80000000u : 0u);
+                    seen[r0] = (int)lvl;
                     cn[at] = (unsigned char)g.pool_cn[e];
                     const int l = g.pool_str_off[e + 1] - g.pool_str_off[e];
                     if (soff) { soff[at] = (unsigned)at_c; len[at] = (unsigned char)l; }
@@ -1059,6 +1070,7 @@ struct Engine
             w.end_node = s.g->end_node;
             w.n_levels = p.n_levels;
             w.lvl_ent_off = reinterpret_cast<const int*>(Dst + p.o_lvl);
+            w.lvl_dup = reinterpret_cast<const unsigned char*>(Dst + p.o_dup);
             w.ent_rid = reinterpret_cast<const unsigned*>(Dst + p.o_rid);
             w.ent_cn = reinterpret_cast<const unsigned char*>(Dst + p.o_cn);
             w.ent_soff = p.multi ? reinterpret_cast<const unsigned*>(Dst + p.o_soff) : nullptr;
@@ -1084,6 +1096,7 @@ struct Engine
             w.ab_io = reinterpret_cast<double*>(Dsc + p.d_ab);
             w.ops = reinterpret_cast<int2*>(Dsc + p.d_ops);
             w.kid_ab = reinterpret_cast<double*>(Dsc + p.d_kid);
+            w.lut = reinterpret_cast<double*>(Dsc + p.d_lut);
             w.res = d_walk_res.p + k;
             w.paths = reinterpret_cast<int*>(Dsc + p.d_paths);
             w.final_slot = d_final_slot.p + k * WALK_SMAX;
@@ -1094,19 +1107,13 @@ struct Engine
         d_walk.reserve(hs.size());
         RAMBL_CUDA(cudaMemcpyAsync(d_walk.p, hs.data(), sizeof(WalkSub) * hs.size(), cudaMemcpyHostToDevice, st));
         stats.h2d_bytes += (long long)(sizeof(WalkSub) * hs.size());
-        // ---- CTA shape: as many warps (32-draw blocks per Gibbs round) as still let every subgroup be resident,
-        // then the widest weight tiles that fit (levels with more strains read their weights from L1/L2)
+        // ---- CTA shape.  Measured on 500 subgroups: eight warps per subgroup with one subgroup per SM
+        // beat two or four warps with all subgroups resident at once -- a chain is latency-bound, and a round that
+        // speculates over 256 draws makes up for the waves -- so the CTA is always eight warps wide, with the widest
+        // weight tiles that fit next to the per-strain arrays.
         const size_t sm_bytes = 227 * 1024;
-        int nb = 8, tile = 32;
-        for (; nb > 1; nb >>= 1)
-            if (148 * (sm_bytes / walk_smem_bytes(nb, 32)) >= take.size()) break;
-        if (forced_nb > 0) nb = forced_nb;
-        {
-            const size_t want = std::max<size_t>(1, (take.size() + 147) / 148);  // CTAs per SM
-            const size_t budget = sm_bytes / std::min<size_t>(want, std::max<size_t>(1, sm_bytes / walk_smem_bytes(nb, 32)));
-            tile = 32;
-            while (tile + 8 <= WALK_SMAX && walk_smem_bytes(nb, tile + 8) <= budget) tile += 8;
-        }
+        int nb = forced_nb > 0 ? forced_nb : 8, tile = 8;
+        while (tile + 4 <= WALK_SMAX && walk_smem_bytes(nb, tile + 4) <= sm_bytes) tile += 4;
         if (forced_tile > 0) tile = forced_tile;
         WalkParams wp;
         wp.n = prm.n;

@@ -32,6 +32,7 @@ struct WalkShared  // carved out of dynamic shared memory after the Gibbs arrays
     int* lab_off;           // [SMAX]
     int* lab_len;           // [SMAX]
     int* idx;               // [SMAX] kept candidates, in order
+    int* la;                // [SMAX] letter code of a one-letter strain label, 8 for a collapsed node
     unsigned char* parent_used;  // [SMAX]
     int* v;                 // scalars shared by the CTA (V_*)
 };
@@ -68,7 +69,7 @@ size_t walk_smem_bytes(int nb, int tile_S)
     b += al(sizeof(double) * (size_t)nb * 36) + al(sizeof(double) * (size_t)nb * 8);
     b += al(sizeof(unsigned long long) * WALK_SMAX);
     b += 3 * al(sizeof(double) * WALK_SMAX);
-    b += 4 * al(sizeof(int) * WALK_SMAX);
+    b += 5 * al(sizeof(int) * WALK_SMAX);
     b += al(WALK_SMAX);
     b += al(sizeof(int) * 16);
     return b + 128;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
     ws.lab_off = carve<int>(sp, WALK_SMAX);
     ws.lab_len = carve<int>(sp, WALK_SMAX);
     ws.idx = carve<int>(sp, WALK_SMAX);
+    ws.la = carve<int>(sp, WALK_SMAX);
     ws.parent_used = carve<unsigned char>(sp, WALK_SMAX);
     ws.v = carve<int>(sp, 16);
 
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
     const int end_node = w->end_node;
     const int n_levels = w->n_levels;
     const int* const lvl_ent_off = w->lvl_ent_off;
+    const unsigned char* const lvl_dup = w->lvl_dup;
     const unsigned* const ent_rid = w->ent_rid;
     const unsigned char* const ent_cn = w->ent_cn;
     const unsigned* const ent_soff = w->ent_soff;
@@ -143,6 +146,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
     double* const ab_io = w->ab_io;
     int2* const ops = w->ops;
     double* const kid_ab = w->kid_ab;
+    double* const lut_g = w->lut;
     WalkResult* const res = w->res;
 
     unsigned uses0 = 0, uses1 = 0;
@@ -179,9 +183,16 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
         for (int o = 0; o < n_ops; ++o)
         {
             const int2 op = ops[o];
-            const double* src = ll + (long long)op.x * R;
-            double* dst = ll + (long long)op.y * R;
-            for (int x = tid; x < R; x += NT) dst[x] = src[x];
+            const double* __restrict__ src = ll + (long long)op.x * R;  // distinct slots: the rows never overlap
+            double* __restrict__ dst = ll + (long long)op.y * R;
+            for (int x = tid; x < R; x += 4 * NT)
+            {
+                double v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = (x + k * NT < R) ? src[x + k * NT] : 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (x + k * NT < R) dst[x + k * NT] = v[k];
+            }
             for (int q = tid; q < 36; q += NT) sub[(long long)op.y * 36 + q] = sub[(long long)op.x * 36 + q];
         }
         if (level == n_levels - 1) break;  // "$": the host closes the result (sort + merge_strains)
@@ -233,8 +244,9 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
             // "new" = first time any strain sees the read; hard_clustering only looks at the flag on collapsed nodes
             for (int r = tid; r < m; r += NT)
             {
-                const int rid = (int)ent_rid[e0 + r];
-                const unsigned char f = present[rid] ? 0 : 1;
+                const unsigned er = ent_rid[e0 + r];
+                const int rid = (int)(er & 0x7fffffffu);
+                const unsigned char f = ((er >> 31) || present[rid]) ? 0 : 1;  // a second entry of the read on this level: not new
                 present[rid] = 1;
                 fresh[r] = (mode == MODE_HARD && !any_multi) ? 0 : f;
                 const int cn = (int)ent_cn[e0 + r], d0 = ent_doff[r], po = pair_off[rid];
@@ -264,52 +276,81 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
             }
             nsweeps = (mode == MODE_GIBBS) ? min(prm.n, 40000 / max(D, 1)) : 0;
             // ---- log-likelihood update: ll[strain][read] += log p(read letters | strain letters)
-            for (int s = warp; s < S; s += NB)
+            // the strains' log tables first (Strain::logprob(a,b) = log(sub[a,b]) - log(comp[a]), Strain.cpp:130-133) ...
+            for (int q = tid; q < S * 36; q += NT)
             {
-                double* lut = ws.lut + warp * 36;
-                double* comp = ws.comp + warp * 8;
-                const double* sb = sub + (long long)ws.slot[s] * 36;
-                if (lane < 6)
+                const int st = q / 36, k = q - st * 36;
+                const double* sb = sub + (long long)ws.slot[st] * 36;
+                double c = 0;
+                for (int j = 0; j < 6; ++j) c += sb[(k / 6) * 6 + j];
+                lut_g[q] = log(sb[k]) - log(c);
+            }
+            for (int st = tid; st < S; st += NT) ws.la[st] = (ws.lab_len[st] == 1) ? letter_code(label_chars[ws.lab_off[st]]) : 8;
+            __syncthreads();
+            // ... then one thread per read-pool entry, four strains in flight (independent rows): a read has one entry per
+            // level, except the entries flagged as repeats, which are added afterwards in entry order
+            auto entry_term = [&](int st, int r, const char* rs, int rl) -> double {
+                const double* lut = lut_g + st * 36;
+                const int la = ws.la[st];
+                if (la < 8)
                 {
-                    double c = 0;
-                    for (int j = 0; j < 6; ++j) c += sb[lane * 6 + j];
-                    comp[lane] = c;
+                    if (rl == 1) return pair_loglik(lut, la, letter_code(rs[0]));
+                    return (la < 6) ? -INFINITY : NAN;  // one strain letter against a multi-letter key
                 }
-                __syncwarp();
-                for (int q = lane; q < 36; q += 32) lut[q] = log(sb[q]) - log(comp[q / 6]);
-                __syncwarp();
-                double* row = ll + (long long)ws.slot[s] * R;
-                const char* lab = label_chars + ws.lab_off[s];
-                const int lab_l = ws.lab_len[s];
-                for (int r = lane; r < m; r += 32)
+                const char* lab = label_chars + ws.lab_off[st];
+                const int lab_l = ws.lab_len[st];
+                double d = 0;
+                if (fresh[r])
+                {   // the read starts inside this collapsed node: align the tails (lines 364-375)
+                    int ii = lab_l, jj = rl;
+                    while (ii > 0 && jj > 0) d += pair_loglik(lut, letter_code(lab[--ii]), letter_code(rs[--jj]));
+                }
+                else
+                {   // the read was already running: align the heads (lines 376-387)
+                    int ii = 0, jj = 0;
+                    while (ii < lab_l && jj < rl) d += pair_loglik(lut, letter_code(lab[ii++]), letter_code(rs[jj++]));
+                }
+                return d;
+            };
+            for (int r = tid; r < m; r += NT)
+            {
+                const unsigned er = ent_rid[e0 + r];
+                if (er >> 31) continue;
+                const int rid = (int)er;
+                const char* rs = ent_chars + (ent_soff ? ent_soff[e0 + r] : (unsigned)(e0 + r));
+                const int rl = ent_len ? (int)ent_len[e0 + r] : 1;
+                for (int s0 = 0; s0 < S; s0 += 4)
                 {
-                    const int rid = (int)ent_rid[e0 + r];
-                    const char* rs = ent_chars + (ent_soff ? ent_soff[e0 + r] : (unsigned)(e0 + r));
-                    const int rl = ent_len ? (int)ent_len[e0 + r] : 1;
-                    double d;
-                    if (lab_l == 1)
+                    double dv[4], old[4];
+                    double* pr[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
                     {
-                        const int a = letter_code(lab[0]);
-                        if (rl == 1) d = pair_loglik(lut, a, letter_code(rs[0]));
-                        else d = (a < 6) ? -INFINITY : NAN;  // one strain letter against a multi-letter key
+                        const int st = min(s0 + k, S - 1);
+                        dv[k] = entry_term(st, r, rs, rl);
+                        pr[k] = ll + (long long)ws.slot[st] * R + rid;
                     }
-                    else
-                    {
-                        d = 0;
-                        if (fresh[r])
-                        {   // the read starts inside this collapsed node: align the tails (lines 364-375)
-                            int ii = lab_l, jj = rl;
-                            while (ii > 0 && jj > 0) d += pair_loglik(lut, letter_code(lab[--ii]), letter_code(rs[--jj]));
-                        }
-                        else
-                        {   // the read was already running: align the heads (lines 376-387)
-                            int ii = 0, jj = 0;
-                            while (ii < lab_l && jj < rl) d += pair_loglik(lut, letter_code(lab[ii++]), letter_code(rs[jj++]));
-                        }
-                    }
-                    row[rid] += d;  // a read has one entry per level (checked when the tables are built)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) old[k] = *pr[k];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (s0 + k < S) *pr[k] = old[k] + dv[k];
                 }
-                __syncwarp();
+            }
+            if (lvl_dup[level])
+            {
+                __syncthreads();
+                for (int st = tid; st < S; st += NT)
+                {
+                    double* row = ll + (long long)ws.slot[st] * R;
+                    for (int r = 0; r < m; ++r)
+                    {
+                        const unsigned er = ent_rid[e0 + r];
+                        if (!(er >> 31)) continue;
+                        const char* rs = ent_chars + (ent_soff ? ent_soff[e0 + r] : (unsigned)(e0 + r));
+                        row[er & 0x7fffffffu] += entry_term(st, r, rs, ent_len ? (int)ent_len[e0 + r] : 1);
+                    }
+                }
             }
             __syncthreads();
             // ---- weights: exp(loglik(read) + loglik(mate)) per (draw, strain), tile-major (dpm_dev.cuh)
@@ -319,7 +360,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
             for (int d = tid; d < D; d += NT)
             {
                 const int r = draw_entry[d];
-                const int rid = (int)ent_rid[e0 + r];
+                const int rid = (int)(ent_rid[e0 + r] & 0x7fffffffu);
                 const int mate = draw_mate[d];
                 for (int s0 = 0; s0 < S; s0 += 4)
                 {

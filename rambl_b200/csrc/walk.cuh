@@ -63,7 +63,8 @@ struct WalkSub
     int end_node;
     int n_levels;                   // levels of the walk; the last one holds "$" alone
     const int* lvl_ent_off;         // [n_levels+1] read-pool entries of a level, in the order the level's nodes list them
-    const unsigned* ent_rid;        // [entries] unique read id
+    const unsigned char* lvl_dup;   // [n_levels] some read has more than one entry on the level
+    const unsigned* ent_rid;        // [entries] unique read id; bit 31: a further entry of a read already listed on this level
     const unsigned char* ent_cn;    // [entries] copies
     const unsigned* ent_soff;       // [entries] offset of the entry's letters in ent_chars, or null: offset == index
     const unsigned char* ent_len;   // [entries] letters, or null: 1
@@ -89,6 +90,7 @@ struct WalkSub
     double* ab_io;                  // [WALK_SMAX] abundances in, increments out
     int2* ops;                      // [WALK_KMAX] slot copies queued by the last extension
     double* kid_ab;                 // [WALK_KMAX] scratch of the cut
+    double* lut;                    // [WALK_SMAX][36] log substitution tables of the level's strains
     // ---- result
     WalkResult* res;
     int* paths;                     // [<= WALK_SMAX][n_levels] node ids of the final candidates' paths

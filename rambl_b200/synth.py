@@ -83,6 +83,23 @@ class Subgroup:
     def n_unique(self) -> int:
         return len(self.pos)
 
+    def packed(self) -> dict:
+        """The reads as host buffers: positions and copies as int32 arrays, CIGARs and letters as byte arenas with
+        int64 offsets (what rambl_batch_add_subgroup_packed takes).  Built once and kept."""
+        pk = self.__dict__.get("_packed")
+        if pk is None:
+            def arena(strs):
+                off = np.zeros(len(strs) + 1, dtype=np.int64)
+                if strs:
+                    off[1:] = np.cumsum([len(x) for x in strs])
+                return off, "".join(strs).encode()
+            co, cc = arena(self.cigar)
+            so, sc = arena(self.seq)
+            pk = dict(pos=np.asarray(self.pos, dtype=np.int32), cn=np.asarray(self.cn, dtype=np.int32),
+                      cigar_off=co, cigar_chars=cc, seq_off=so, seq_chars=sc)
+            self.__dict__["_packed"] = pk
+        return pk
+
     @property
     def n_reads(self) -> int:
         return int(sum(self.cn))
