@@ -73,6 +73,9 @@ int rambl_set_gibbs_blocks(int32_t blocks);
  * kernel (1, 2, 4, 8; 0 = by batch size).  Both paths compute the same chains: measurement and test hooks. */
 int rambl_set_walk_mode(int32_t mode);
 int rambl_set_walk_blocks(int32_t blocks);
+/* CTAs per subgroup of the walk kernel: a thread-block cluster whose extra CTAs join the Gibbs chains over
+ * distributed shared memory (1, 2, 4, 8; 0 = by batch size: clusters when the batch has fewer subgroups than SMs). */
+int rambl_set_walk_cluster(int32_t ctas);
 /* Host worker threads for the per-subgroup host work (graph construction, staging).  0 = $RAMBL_HOST_THREADS if
  * set, else one per hardware thread.  scripts/rambl.py's `--cores` (rambl.py:179) is the natural value; several
  * processes sharing a box (one per GPU) should each take their share. */

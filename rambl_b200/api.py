@@ -60,6 +60,7 @@ SYMBOLS = {
     "rambl_set_host_threads": (C.c_int, [C.c_int32]),
     "rambl_set_walk_mode": (C.c_int, [C.c_int32]),
     "rambl_set_walk_blocks": (C.c_int, [C.c_int32]),
+    "rambl_set_walk_cluster": (C.c_int, [C.c_int32]),
     "rambl_msa_rows_capacity": (C.c_int64, [C.c_int32, _i32p, _i32p]),
     "rambl_msa_sp_align_batch": (C.c_int, [C.c_int32, _i32p, _i32p, C.c_char_p, _i32p, _i64p, _i32p, C.c_char_p,
                                            C.POINTER(C.c_uint64), C.POINTER(C.c_float)]),

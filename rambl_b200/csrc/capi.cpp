@@ -242,6 +242,13 @@ int rambl_set_walk_blocks(int32_t blocks)
     return RAMBL_OK;
 }
 
+int rambl_set_walk_cluster(int32_t ctas)
+{
+    if (ctas != 0 && ctas != 1 && ctas != 2 && ctas != 4 && ctas != 8) return RAMBL_ERR_INVALID;
+    set_walk_cluster(ctas);
+    return RAMBL_OK;
+}
+
 int rambl_set_host_threads(int32_t n)
 {
     if (n < 0) return RAMBL_ERR_INVALID;

@@ -88,6 +88,50 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- thread-block clusters: rank, distributed shared memory, cluster barrier
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_id_x()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+// the shared::cluster address of `p` (a shared-memory address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ unsigned dsmem_addr(const void* p, unsigned rank)
+{
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void dsmem_st_u16(unsigned addr, unsigned short v)
+{
+    asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ void dsmem_st_u32(unsigned addr, unsigned v)
+{
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void dsmem_add_u32(unsigned addr, unsigned v)
+{
+    asm volatile("red.shared::cluster.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr int GIBBS_CMAX = 8;  // CTAs per cluster (the portable maximum)
+
 // The same chain with ONE warp per 32-draw block and up to eight blocks (256 draws) per round, for levels of
 // at most 128 candidate strains (the reference prunes to about 80 and usually holds 10-50).  A warp keeps its
 // block to itself -- no partial sums to exchange, no barriers inside a block -- and spends about a third of
@@ -114,6 +158,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // (the caller guarantees S <= tile_S); otherwise a level with S > tile_S reads its weights straight from global
 // memory (L1/L2), no staging.  On return (after a CTA barrier) masses[0..S) holds the final masses and cnt the letter
 // counts per strain.
+//
+// CL: the chain runs on a thread-block CLUSTER of `csize` CTAs (rank `crank`), one SM each -- csize * nb blocks per
+// round, block rank * nb + b on warp b of CTA `rank`.  A draw is corrected by the picks of every earlier block of the
+// round: the blocks of its own CTA as before, the CTAs of lower rank through their per-strain TOTALS, which every CTA
+// writes into every other CTA's shared memory (distributed shared memory) once per pass, together with its verdict
+// on the previous pass ("one of my picks moved"); one cluster barrier per pass.  A round is over when no CTA moved a
+// pick, which every CTA learns from the same flags, so all of them leave the loop together.  Every CTA keeps its own
+// copy of the masses (updated from all totals), stages its own tiles, and counts the letters of its own draws (summed
+// into rank 0 at the end).
 struct GibbsShared
 {
     double* wbuf;                 // [2][wbuf_doubles / 2] weight tiles of a round, double-buffered (bulk-copied)
@@ -126,18 +179,23 @@ struct GibbsShared
     uint2* lists;                 // [NB][32 * NS + 8] the strains that count for block b
     unsigned* pmask;              // [NB][row_S] lanes of block b that picked s
     int* cnt;                     // [row_S][8] letter counts per strain
+    unsigned short* ctot = nullptr;  // cluster only: [2][GIBBS_CMAX][row_S] picks per strain and CTA in a pass (by pass parity)
+    unsigned* cflag = nullptr;       // cluster only: [2][GIBBS_CMAX] "a pick moved in my last pass"
 };
 
 template <int NS>
 __host__ __device__ constexpr int gibbs_list_len() { return 32 * NS + 8; }  // every strain + padding
 
-template <int NB, int NS, bool STAGED_ONLY>
+template <int NB, int NS, bool STAGED_ONLY, bool CL = false>
 __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& uses0, unsigned& uses1, int nb, int S, int D, int nsweeps,
                                               bool count_letters, const double* wt, const int* code, const double* U,
                                               const double* ab_in, unsigned long long& rounds, unsigned long long& passes,
-                                              unsigned long long* counters)
+                                              unsigned long long* counters, int crank = 0, int csize = 1)
 {
     constexpr int GIBBS_LIST = gibbs_list_len<NS>();
+    if (!CL) { crank = 0; csize = 1; }
+    const int gnb = csize * nb;        // blocks of 32 draws per round, over the whole cluster
+    const int gb0 = crank * nb;        // the first of them that belongs to this CTA
     double* const wbuf = gs.wbuf;
     double* const masses = gs.masses;
     double* const mass0 = gs.mass0;
@@ -162,18 +220,21 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
     }
     __syncthreads();
     // The chain is one stream of tiles: tile T = sweep * tiles + t holds draws 32t..32t+31 of that sweep, and round
-    // r takes tiles r*nb .. r*nb+nb-1 whatever sweep they fall in (the weights of tile t are the same in every
+    // r takes tiles r*gnb .. r*gnb+gnb-1 whatever sweep they fall in (the weights of tile t are the same in every
     // sweep), so only the very last round can be short of blocks.
     const int tiles = Dp / 32;                       // tiles of 32 draws per sweep
     const int total_tiles = (S >= 2) ? nsweeps * tiles : 0;   // <= 5000 sweeps x 40000/32 tiles
-    const int n_rounds = (total_tiles + nb - 1) / nb;
-    int stage_pos = 0;  // tile (within a sweep) the next staged round starts at; thread 0 only
-    // stage the weights of round r: its tiles are contiguous up to the end of a sweep, then wrap to tile 0
+    const int n_rounds = (total_tiles + gnb - 1) / gnb;
+    // rounds in which this CTA has tiles of its own: a prefix of the rounds (only the last round can be short)
+    const int my_rounds = total_tiles > gb0 ? (total_tiles - gb0 + gnb - 1) / gnb : 0;
+    // stage the weights of round r: this CTA's tiles are contiguous up to the end of a sweep, then wrap to tile 0
     auto stage = [&](int r) {
         if (staged && tid == 0)
         {
             const int bf = r & 1;
-            int left = min(nb, total_tiles - r * nb);
+            const int first = r * gnb + gb0;
+            int left = min(nb, total_tiles - first);
+            int stage_pos = first % tiles;
             mbar_expect_tx(&bars[bf], (unsigned)left * (unsigned)S * 256u);
             double* dst = wbuf + (size_t)bf * buf_doubles;
             while (left > 0)
@@ -187,7 +248,7 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
             }
         }
     };
-    if (n_rounds > 0) stage(0);
+    if (my_rounds > 0) stage(0);
     const int Cs = (S + GIBBS_NW - 1) / GIBBS_NW;    // strains per chunk
     const unsigned long long below = (b == 0) ? 0ull : (~0ull >> (64 - 8 * b));  // the bytes of hpack that precede this block
     const unsigned below_lo = (unsigned)below, below_hi = (unsigned)(below >> 32);
@@ -197,22 +258,23 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
 #pragma unroll
     for (int h = 0; h < NS; ++h) tc[h] = 0;
     int c_last = -1;                     // this lane's final pick of the previous round
+    int cpass = 0, cuse = 0;             // cluster: exchanges done so far (their parity picks the buffer), buffer of the last one
     unsigned* pm = pmask + b * smem_S;
     uint2* list = lists + b * GIBBS_LIST;
     // this block's tile of the coming round: sweep and tile within the sweep; its uniform and read letter are
     // fetched from global memory one round ahead
-    int sw_next = 0, t_next = b;
-    while (tiles > 0 && t_next >= tiles) { t_next -= tiles; ++sw_next; }
+    int sw_next = 0, t_next = gb0 + b;
+    if (tiles > 0) { sw_next = t_next / tiles; t_next -= sw_next * tiles; }
     double u_next = 0.0;
     int cd_next = 0;
-    if (b < nb && b < total_tiles && t_next * 32 + lane < D)
+    if (b < nb && gb0 + b < total_tiles && t_next * 32 + lane < D)
     {
         u_next = U[(long long)sw_next * D + t_next * 32 + lane];
         if (count_letters) cd_next = code[t_next * 32 + lane];
     }
     for (int r = 0; r < n_rounds; ++r)
     {
-        const bool active = b < nb && r * nb + b < total_tiles;  // only the last round can leave the high blocks idle
+        const bool active = b < nb && r * gnb + gb0 + b < total_tiles;  // only the last round can leave the high blocks idle
         const int t_cur = t_next;
         const int d = t_cur * 32 + lane;
         const bool valid = active && d < D;
@@ -220,15 +282,15 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
         const int cd = cd_next;
         if (r + 1 < n_rounds)
         {
-            stage(r + 1);  // overlaps this round's arithmetic
-            t_next += nb;
+            if (r + 1 < my_rounds) stage(r + 1);  // overlaps this round's arithmetic
+            t_next += gnb;
             while (t_next >= tiles) { t_next -= tiles; ++sw_next; }
             const int dn = t_next * 32 + lane;
-            const bool vn = b < nb && (r + 1) * nb + b < total_tiles && dn < D;
+            const bool vn = b < nb && (r + 1) * gnb + gb0 + b < total_tiles && dn < D;
             u_next = vn ? U[(long long)sw_next * D + dn] : 0.0;
             cd_next = (vn && count_letters) ? code[dn] : 0;
         }
-        if (staged) mbar_wait(&bars[r & 1], (((r & 1) ? uses1 : uses0) + (unsigned)(r >> 1)) & 1u);
+        if (staged && r < my_rounds) mbar_wait(&bars[r & 1], (((r & 1) ? uses1 : uses0) + (unsigned)(r >> 1)) & 1u);
         unsigned long long* hpack = hpacks + (r & 1) * smem_S;
         unsigned char* hbytes = reinterpret_cast<unsigned char*>(hpack);
         const double* wl = staged ? wbuf + (size_t)(r & 1) * buf_doubles + (size_t)b * S * 32 + lane
@@ -329,6 +391,7 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
         // ---- settle: check every pick against the picks of the earlier draws until nothing moves
         int settle_passes = 0;
         int c_pub = -1;  // what this lane has published
+        int moved_cta = 1;  // the verdict of this CTA's last pass (the first exchange of a round always goes on)
         for (;;)
         {
             if (active)
@@ -344,6 +407,25 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
                 c_pub = c;
             }
             __syncthreads();
+            if (CL)
+            {
+                // this CTA's picks per strain, and its verdict on the previous pass, into every CTA of the cluster
+                unsigned short* tot_row = gs.ctot + ((size_t)(cpass & 1) * GIBBS_CMAX + crank) * smem_S;
+                for (int s = tid; s < S; s += blockDim.x)
+                {
+                    const unsigned long long hp = hpack[s];
+                    const unsigned short t = (unsigned short)__dp4a((unsigned)hp, 0x01010101u, __dp4a((unsigned)(hp >> 32), 0x01010101u, 0u));
+                    for (int k = 0; k < csize; ++k) dsmem_st_u16(dsmem_addr(tot_row + s, (unsigned)k), t);
+                }
+                if (tid < csize) dsmem_st_u32(dsmem_addr(gs.cflag + (cpass & 1) * GIBBS_CMAX + crank, (unsigned)tid), (unsigned)moved_cta);
+                cluster_barrier();
+                cuse = cpass & 1;
+                ++cpass;
+                unsigned any = 0;
+                for (int k = 0; k < csize; ++k) any |= gs.cflag[cuse * GIBBS_CMAX + k];
+                if (!any) break;  // no CTA moved a pick in the last pass: what is published is the chain
+            }
+            const unsigned short* ctot_now = CL ? gs.ctot + (size_t)cuse * GIBBS_CMAX * smem_S : nullptr;
             bool moved = false;
             if (active)
             {
@@ -360,6 +442,8 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
                         const unsigned long long hp = in ? hpack[lane + 32 * h] : 0ull;
                         mm[h] = in ? pm[lane + 32 * h] : 0u;
                         hs[h] = __dp4a((unsigned)hp & below_lo, 0x01010101u, __dp4a((unsigned)(hp >> 32) & below_hi, 0x01010101u, 0u));
+                        if (CL && in)
+                            for (int k = 0; k < crank; ++k) hs[h] += ctot_now[k * smem_S + lane + 32 * h];  // the CTAs before this one
                     }
 #pragma unroll
                     for (int h = 0; h < NS; ++h)
@@ -395,8 +479,10 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
                         p_prev = fma(w4[k], (s < c) ? kd : 0.0, p_prev);
                     }
                 }
-                const int k_c = (int)__dp4a((unsigned)hpc & below_lo, 0x01010101u, __dp4a((unsigned)(hpc >> 32) & below_hi, 0x01010101u, 0u)) +
-                                __popc(mmc & lt);
+                int k_c = (int)__dp4a((unsigned)hpc & below_lo, 0x01010101u, __dp4a((unsigned)(hpc >> 32) & below_hi, 0x01010101u, 0u)) +
+                          __popc(mmc & lt);
+                if (CL)
+                    for (int k = 0; k < crank; ++k) k_c += ctot_now[k * smem_S + cc];
                 const double p_here = fma(w_c, (double)k_c, p_prev);
                 const double thr = u * (base_tot + p_tot);
                 bool ok = true;
@@ -469,9 +555,9 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
             ++passes;
             // draw 32b+j is final after 32b+j+1 passes, so 32*NB+1 passes always suffice -- the cap only guards
             // the device against a launch that does not terminate
-            const int any_moved = __syncthreads_or(moved ? 1 : 0);  // also orders this pass before the next publication
-            if (!any_moved) break;
-            if (++settle_passes > 32 * NB + 8)
+            moved_cta = __syncthreads_or(moved ? 1 : 0);  // also orders this pass before the next publication
+            if (!CL && !moved_cta) break;
+            if (++settle_passes > 32 * NB * csize + 8)
             {   // cannot happen for finite weights; report it instead of committing a round that is not the chain
                 if (tid == 0 && counters) atomicAdd(&counters[2], 1ull);
                 break;
@@ -494,9 +580,13 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
             if (sh < S)
             {
                 const unsigned long long hp = hpack[sh];
-                if (hp)
+                int picks = (int)__dp4a((unsigned)hp, 0x01010101u, __dp4a((unsigned)(hp >> 32), 0x01010101u, 0u));
+                if (CL)
+                    for (int k = 0; k < csize; ++k)
+                        if (k != crank) picks += gs.ctot[((size_t)cuse * GIBBS_CMAX + k) * smem_S + sh];
+                if (picks)
                 {
-                    tc[h] += (int)__dp4a((unsigned)hp, 0x01010101u, __dp4a((unsigned)(hp >> 32), 0x01010101u, 0u));
+                    tc[h] += picks;
                     mass[sh] = mass0[sh] + (double)tc[h];
                 }
             }
@@ -504,10 +594,17 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
         __syncwarp();
     }
     __syncthreads();  // the letter counts of every warp
+    if (CL)
+    {   // the letter counts of the other CTAs' draws go to rank 0
+        if (crank != 0)
+            for (int k = tid; k < S * 8; k += blockDim.x)
+                if (cnt[k]) dsmem_add_u32(dsmem_addr(cnt + k, 0u), (unsigned)cnt[k]);
+        cluster_barrier();
+    }
     if (staged)
     {
-        uses0 += (unsigned)((n_rounds + 1) >> 1);
-        uses1 += (unsigned)(n_rounds >> 1);
+        uses0 += (unsigned)((my_rounds + 1) >> 1);
+        uses1 += (unsigned)(my_rounds >> 1);
     }
 }
 

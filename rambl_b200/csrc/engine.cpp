@@ -856,7 +856,7 @@ struct Engine
         size_t o_label_off = 0, o_out_off = 0, o_out_to = 0, o_out_cover = 0, o_lvl = 0, o_dup = 0, o_rid = 0, o_cn = 0, o_soff = 0,
                o_len = 0, o_chars = 0, o_pair_off = 0, o_pair_val = 0;
         size_t d_present = 0, d_free = 0, d_cand0 = 0, d_cand1 = 0, d_trail = 0, d_W = 0, d_doff = 0, d_dent = 0, d_dmate = 0,
-               d_fresh = 0, d_ab = 0, d_ops = 0, d_kid = 0, d_lut = 0, d_res = 0, d_paths = 0, d_fslot = 0, d_fab = 0;
+               d_fresh = 0, d_ab = 0, d_ops = 0, d_kid = 0, d_lut = 0, d_helper = 0, d_res = 0, d_paths = 0, d_fslot = 0, d_fab = 0;
         int trail_cap = 0;
     };
     std::vector<WalkPlan> plans;
@@ -867,10 +867,12 @@ struct Engine
     DevBuf<int> d_final_slot;
     DevBuf<double> d_final_ab;
 
-    // The walk order of prepare() -- cur = {0}; next = the unseen successors of cur, in order -- is a property of the
-    // graph.  The device walk takes a subgroup when every node sits on exactly one level, "$" ends the walk alone on
-    // the last level, a read has at most one entry per level (the log-likelihood update is then a plain add in a fixed
-    // order) and the entries fit the compact tables; anything else goes through the level-synchronous path.
+    // The walk order of prepare() -- cur = {0}; next = the successors of cur not yet listed for the next level, in
+    // order -- is a property of the graph, not of the candidate strains.  The device walk takes a subgroup when "$" ends
+    // the walk alone on its level and the read-pool entries fit the compact tables; a node reached on two levels
+    // simply has its pool listed on both (as prepare() does), a read with several entries on one level has the later
+    // ones flagged (they are added after the first, in entry order).  Anything else goes through the
+    // level-synchronous path.
     void plan_walk(size_t i)
     {
         const Sub& s = subs[i];
@@ -878,7 +880,7 @@ struct Engine
         const FlatGraph& g = *s.g;
         p = WalkPlan();
         if (g.n_nodes < 2 || g.end_node < 0) { p.reason = 8; return; }
-        std::vector<int> level_of(g.n_nodes, -1);
+        std::vector<int> mark(g.n_nodes, -1);
         std::vector<int> cur(1, 0), nxt;
         std::vector<int> seen_rid(std::max(1, g.n_reads), -1);
         p.lvl_ent_off.assign(1, 0);
@@ -887,13 +889,12 @@ struct Engine
         while (!cur.empty() && ok)
         {
             if (ended) { ok = false; p.reason = 2; break; }  // something follows "$"
+            if (level > g.n_nodes + 1) { ok = false; p.reason = 1; break; }  // not a DAG
             long long m = 0, D = 0;
             unsigned char dup = 0;
             nxt.clear();
             for (int u : cur)
             {
-                if (level_of[u] >= 0) { ok = false; p.reason = 1; break; }
-                level_of[u] = level;
                 if (u == g.end_node) { if (cur.size() != 1) { ok = false; p.reason = 2; } ended = true; }
                 else if (u != 0)
                     for (int e = g.pool_off[u]; e < g.pool_off[u + 1]; ++e)
@@ -905,18 +906,16 @@ struct Engine
                         if (len > 1) p.multi = true;
                         m += 1; D += cn; p.n_chars += len;
                     }
-                else if (g.pool_off[1] != g.pool_off[0]) { ok = false; p.reason = 5; }  // "^" carries no reads
+                else if (g.pool_off[1] != g.pool_off[0] || level != 0) { ok = false; p.reason = 5; }  // "^" carries no reads
                 if (!ok) break;
                 p.order.push_back(u);
                 for (int e = g.out_off[u]; e < g.out_off[u + 1]; ++e)
                 {
                     const int v = g.out_to[e];
-                    if (level_of[v] == -1) { level_of[v] = -2 - level; nxt.push_back(v); }
-                    else if (level_of[v] != -2 - level) { ok = false; p.reason = 1; break; }  // reached again from another level
+                    if (mark[v] != level) { mark[v] = level; nxt.push_back(v); }
                 }
             }
             if (!ok) break;
-            for (int v : nxt) level_of[v] = -1;
             p.n_ent += m;
             p.lvl_ent_off.push_back((int)p.n_ent);
             p.lvl_dup.push_back(dup);
@@ -936,7 +935,7 @@ struct Engine
     static size_t up16(size_t b) { return (b + 15) & ~size_t(15); }
 
     // Returns the number of subgroups handed to the device walk; on return their Sub holds the closed result.
-    int run_walk(int forced_nb, int forced_tile)
+    int run_walk(int forced_nb, int forced_tile, int forced_cluster)
     {
         const size_t n = subs.size();
         plans.assign(n, WalkPlan());
@@ -985,6 +984,7 @@ struct Engine
             scr(p.d_ops, sizeof(int2) * WALK_KMAX);
             scr(p.d_kid, sizeof(double) * WALK_KMAX);
             scr(p.d_lut, sizeof(double) * WALK_SMAX * 36);
+            scr(p.d_helper, sizeof(int) * 4);
             scr(p.d_paths, sizeof(int) * (size_t)WALK_SMAX * p.n_levels);
         }
         if (getenv("RAMBL_TRACE") && take.size() < n)
@@ -1097,6 +1097,7 @@ struct Engine
             w.ops = reinterpret_cast<int2*>(Dsc + p.d_ops);
             w.kid_ab = reinterpret_cast<double*>(Dsc + p.d_kid);
             w.lut = reinterpret_cast<double*>(Dsc + p.d_lut);
+            w.helper = reinterpret_cast<int*>(Dsc + p.d_helper);
             w.res = d_walk_res.p + k;
             w.paths = reinterpret_cast<int*>(Dsc + p.d_paths);
             w.final_slot = d_final_slot.p + k * WALK_SMAX;
@@ -1111,9 +1112,19 @@ struct Engine
         // beat two or four warps with all subgroups resident at once -- a chain is latency-bound, and a round that
         // speculates over 256 draws makes up for the waves -- so the CTA is always eight warps wide, with the widest
         // weight tiles that fit next to the per-strain arrays.
+        // A batch with fewer subgroups than SMs gives every subgroup a CLUSTER of CTAs: the extra CTAs join the Gibbs
+        // chains (more 32-draw blocks per round), the one sequential part of a level.
         const size_t sm_bytes = 227 * 1024;
         int nb = forced_nb > 0 ? forced_nb : 8, tile = 8;
-        while (tile + 4 <= WALK_SMAX && walk_smem_bytes(nb, tile + 4) <= sm_bytes) tile += 4;
+        int cluster = 1;
+        if (nb == 8)
+        {
+            if (take.size() <= 16) cluster = 8;
+            else if (take.size() <= 32) cluster = 4;
+            else if (take.size() <= 72) cluster = 2;
+            if (forced_cluster > 0) cluster = forced_cluster;
+        }
+        while (tile + 4 <= WALK_SMAX && walk_smem_bytes(nb, tile + 4, cluster > 1) <= sm_bytes) tile += 4;
         if (forced_tile > 0) tile = forced_tile;
         WalkParams wp;
         wp.n = prm.n;
@@ -1124,7 +1135,7 @@ struct Engine
         RAMBL_CUDA(cudaEventCreate(&e0));
         RAMBL_CUDA(cudaEventCreate(&e1));
         RAMBL_CUDA(cudaEventRecord(e0, st));
-        launch_walk(d_walk.p, (int)take.size(), wp, nb, tile, st, &stats.launches);
+        launch_walk(d_walk.p, (int)take.size(), wp, nb, tile, cluster, st, &stats.launches);
         RAMBL_CUDA(cudaEventRecord(e1, st));
         // ---- results
         std::vector<WalkResult> res(take.size());
@@ -1143,8 +1154,8 @@ struct Engine
         stats.walk_launches += 1;
         stats.level_steps += max_levels;
         if (getenv("RAMBL_TRACE"))
-            fprintf(stderr, "[rambl] device walk: %zu subgroups, %d warps per CTA, tiles of %d strains, %zu B shared, %.1f ms, "
-                            "tables %.1f MB, scratch %.1f MB\n", take.size(), nb, tile, walk_smem_bytes(nb, tile), ms,
+            fprintf(stderr, "[rambl] device walk: %zu subgroups, %d warps per CTA, %d CTAs per subgroup, tiles of %d strains, %zu B shared, %.1f ms, "
+                            "tables %.1f MB, scratch %.1f MB\n", take.size(), nb, cluster, tile, walk_smem_bytes(nb, tile, cluster > 1), ms,
                     stat_bytes / 1e6, scr_bytes / 1e6);
         std::vector<std::vector<int>> h_paths(take.size());
         for (size_t k = 0; k < take.size(); ++k)
@@ -1218,7 +1229,9 @@ struct Engine
 
 }  // namespace
 
-static int g_walk_mode = 1, g_walk_blocks = 0;
+static int g_walk_mode = 1, g_walk_blocks = 0, g_walk_cluster = 0;
+void set_walk_cluster(int c) { g_walk_cluster = c; }
+int walk_cluster() { return g_walk_cluster; }
 void set_walk_mode(int mode) { g_walk_mode = mode; }
 int walk_mode() { return g_walk_mode; }
 void set_walk_blocks(int nb) { g_walk_blocks = nb; }
@@ -1269,7 +1282,8 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
         {
             const char* enb = getenv("RAMBL_WALK_NB");
             const char* eti = getenv("RAMBL_WALK_TILE");
-            const int taken = E.run_walk(enb ? atoi(enb) : walk_blocks(), eti ? atoi(eti) : 0);
+            const char* ecl = getenv("RAMBL_WALK_CLUSTER");
+            const int taken = E.run_walk(enb ? atoi(enb) : walk_blocks(), eti ? atoi(eti) : 0, ecl ? atoi(ecl) : walk_cluster());
             if (getenv("RAMBL_TRACE")) fprintf(stderr, "[rambl] device walk solved %d of %zu subgroups, until %.1f ms\n", taken, E.subs.size(), since(w0));
         }
     }

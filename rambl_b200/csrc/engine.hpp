@@ -74,6 +74,10 @@ int walk_mode();
 // warps per CTA of the walk kernel (= 32-draw blocks per Gibbs round): 0 = by batch size, else 1, 2, 4 or 8
 void set_walk_blocks(int nb);
 int walk_blocks();
+// CTAs per subgroup of the walk kernel (a thread-block cluster; the extra CTAs join the Gibbs chains): 0 = by batch
+// size, else 1, 2, 4 or 8
+void set_walk_cluster(int c);
+int walk_cluster();
 
 void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, std::vector<SubgroupResult>& out,
                  EngineStats& stats, cudaStream_t stream = 0);

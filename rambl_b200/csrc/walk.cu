@@ -9,6 +9,7 @@
 #include "walk.cuh"
 
 #include <algorithm>
+#include <cstring>
 
 #include "common.hpp"
 #include "dpm_dev.cuh"
@@ -54,7 +55,7 @@ __device__ __forceinline__ T* carve(unsigned char*& p, size_t n)
 
 }  // namespace
 
-size_t walk_smem_bytes(int nb, int tile_S)
+size_t walk_smem_bytes(int nb, int tile_S, bool cluster)
 {
     auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
     size_t b = 0;
@@ -72,17 +73,23 @@ size_t walk_smem_bytes(int nb, int tile_S)
     b += 5 * al(sizeof(int) * WALK_SMAX);
     b += al(WALK_SMAX);
     b += al(sizeof(int) * 16);
+    if (cluster) b += al(sizeof(unsigned short) * 2 * GIBBS_CMAX * WALK_SMAX) + al(sizeof(unsigned) * 2 * GIBBS_CMAX);
     return b + 128;
 }
 
 namespace {
 
-template <int NB>
+// CL: one CLUSTER of CTAs per subgroup.  Rank 0 walks the graph exactly as the single-CTA kernel does; the other
+// ranks wait at a cluster barrier and join for the Gibbs chains only, each adding NB blocks of 32 draws to a round
+// (gibbs_w_chain<.., CL = true>): the chain is the one part of a level that is sequential, so it is the part that
+// gets the extra SMs when a batch has fewer subgroups than the GPU has SMs.
+template <int NB, bool CL>
 __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const WalkSub* __restrict__ subs, WalkParams prm, int tile_S)
 {
     constexpr int NS = 4;
     constexpr int NT = 32 * NB;
-    const WalkSub* __restrict__ w = subs + blockIdx.x;
+    const int crank = CL ? (int)cluster_ctarank() : 0, csize = CL ? (int)cluster_nctarank() : 1;
+    const WalkSub* __restrict__ w = subs + (CL ? cluster_id_x() : blockIdx.x);
     extern __shared__ __align__(128) unsigned char walk_smem[];
     unsigned char* sp = walk_smem;
     GibbsShared gs;
@@ -96,6 +103,11 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
     gs.lists = carve<uint2>(sp, (size_t)NB * gibbs_list_len<NS>());
     gs.pmask = carve<unsigned>(sp, (size_t)NB * WALK_SMAX);
     gs.cnt = carve<int>(sp, WALK_SMAX * 8);
+    if (CL)
+    {
+        gs.ctot = carve<unsigned short>(sp, 2 * GIBBS_CMAX * WALK_SMAX);
+        gs.cflag = carve<unsigned>(sp, 2 * GIBBS_CMAX);
+    }
     WalkShared ws;
     ws.lut = carve<double>(sp, (size_t)NB * 36);
     ws.comp = carve<double>(sp, (size_t)NB * 8);
@@ -154,6 +166,26 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
     long long n_draws = 0, n_updates = 0, n_pairs = 0, n_gbytes = 0, sum_S = 0;  // thread 0 only
     int n_glev = 0, n_unstaged = 0, max_S = 0;
 
+    int* const helper = w->helper;
+    if (CL && crank != 0)
+    {
+        // ---- a helper CTA: nothing but the Gibbs chains of its subgroup, as block rank * NB .. of every round
+        if (tid == 0) { mbar_init(&gs.bars[0], 1); mbar_init(&gs.bars[1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+        for (;;)
+        {
+            cluster_barrier();  // rank 0 has published the next chain (or the end of the walk)
+            if (__ldcg(helper) == 0) break;
+            const int S = __ldcg(helper + 1), D = __ldcg(helper + 2), nsweeps = __ldcg(helper + 3);
+            double* const norms = W + (long long)S * padded_draws(D);
+            int nb = (int)min((size_t)NB, gs.wbuf_doubles / (2 * (size_t)S * 32));
+            if (nb == 0) nb = NB;
+            gibbs_w_chain<NB, NS, false, CL>(gs, uses0, uses1, nb, S, D, nsweeps, true, W, reinterpret_cast<int*>(norms + D),
+                                             prm.uniforms, ab_io, rounds, passes, prm.counters, crank, csize);
+        }
+        return;
+    }
     if (tid == 0)
     {
         mbar_init(&gs.bars[0], 1);
@@ -460,8 +492,13 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                 // for even one block reads its weights from L1/L2 with all NB blocks
                 int nb = (int)min((size_t)NB, gs.wbuf_doubles / (2 * (size_t)S * 32));
                 if (nb == 0) nb = NB;
-                gibbs_w_chain<NB, NS, false>(gs, uses0, uses1, nb, S, D, nsweeps, true, wt, codes, prm.uniforms, ab_io, rounds, passes,
-                                             prm.counters);
+                if (CL)
+                {   // the helper CTAs of the cluster join for the chain
+                    if (tid == 0) { helper[1] = S; helper[2] = D; helper[3] = nsweeps; helper[0] = 1; }
+                    cluster_barrier();
+                }
+                gibbs_w_chain<NB, NS, false, CL>(gs, uses0, uses1, nb, S, D, nsweeps, true, wt, codes, prm.uniforms, ab_io, rounds, passes,
+                                                 prm.counters, crank, csize);
                 if (warp == 0)
                 {   // normalise the masses; fold the averaged letter counts into the models (lines 217-243)
                     const double* mass = gs.masses;
@@ -736,34 +773,59 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
             atomicAdd(&prm.counters[0], rounds);
             atomicAdd(&prm.counters[1], passes);
         }
+        if (CL) helper[0] = 0;  // the walk is over: release the helper CTAs
     }
+    if (CL) cluster_barrier();
 }
 
-template <int NB>
-void launch_walk_nb(const WalkSub* d_subs, int n_subs, const WalkParams& prm, int tile_S, cudaStream_t st)
+template <int NB, bool CL>
+void launch_walk_nb(const WalkSub* d_subs, int n_subs, const WalkParams& prm, int tile_S, int cluster, cudaStream_t st)
 {
-    const size_t smem = walk_smem_bytes(NB, tile_S);
+    const size_t smem = walk_smem_bytes(NB, tile_S, CL);
     static size_t configured = 0;
     if (smem > configured)
     {
-        RAMBL_CUDA(cudaFuncSetAttribute(k_walk<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RAMBL_CUDA(cudaFuncSetAttribute(k_walk<NB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    k_walk<NB><<<n_subs, 32 * NB, smem, st>>>(d_subs, prm, tile_S);
+    if (!CL)
+    {
+        k_walk<NB, CL><<<n_subs, 32 * NB, smem, st>>>(d_subs, prm, tile_S);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_subs * cluster));
+    cfg.blockDim = dim3(32 * NB);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    RAMBL_CUDA(cudaLaunchKernelEx(&cfg, k_walk<NB, CL>, d_subs, prm, tile_S));
 }
 
 }  // namespace
 
-void launch_walk(const WalkSub* d_subs, int n_subs, const WalkParams& prm, int nb, int tile_S, cudaStream_t st, int* launches)
+void launch_walk(const WalkSub* d_subs, int n_subs, const WalkParams& prm, int nb, int tile_S, int cluster, cudaStream_t st, int* launches)
 {
     if (n_subs <= 0) return;
-    switch (nb)
+    if (cluster > 1)
     {
-        case 8: launch_walk_nb<8>(d_subs, n_subs, prm, tile_S, st); break;
-        case 4: launch_walk_nb<4>(d_subs, n_subs, prm, tile_S, st); break;
-        case 2: launch_walk_nb<2>(d_subs, n_subs, prm, tile_S, st); break;
-        default: launch_walk_nb<1>(d_subs, n_subs, prm, tile_S, st); break;
+        if (nb != 8 || cluster > GIBBS_CMAX) throw Error(RAMBL_ERR_INVALID, "clusters need eight-warp CTAs and at most eight CTAs");
+        launch_walk_nb<8, true>(d_subs, n_subs, prm, tile_S, cluster, st);
     }
+    else
+        switch (nb)
+        {
+            case 8: launch_walk_nb<8, false>(d_subs, n_subs, prm, tile_S, 1, st); break;
+            case 4: launch_walk_nb<4, false>(d_subs, n_subs, prm, tile_S, 1, st); break;
+            case 2: launch_walk_nb<2, false>(d_subs, n_subs, prm, tile_S, 1, st); break;
+            default: launch_walk_nb<1, false>(d_subs, n_subs, prm, tile_S, 1, st); break;
+        }
     ++*launches;
     RAMBL_CUDA(cudaGetLastError());
 }

@@ -91,6 +91,7 @@ struct WalkSub
     int2* ops;                      // [WALK_KMAX] slot copies queued by the last extension
     double* kid_ab;                 // [WALK_KMAX] scratch of the cut
     double* lut;                    // [WALK_SMAX][36] log substitution tables of the level's strains
+    int* helper;                    // [4] cluster launches: what rank 0 tells the helper CTAs (0 = the walk is over | 1, S, D, sweeps)
     // ---- result
     WalkResult* res;
     int* paths;                     // [<= WALK_SMAX][n_levels] node ids of the final candidates' paths
@@ -106,8 +107,10 @@ struct WalkParams
     unsigned long long* counters;         // [0] rounds, [1] passes, [2] rounds that did not settle
 };
 
-size_t walk_smem_bytes(int nb, int tile_S);
-// launches k_walk<nb> with one CTA per subgroup; nb = warps per CTA = 32-draw blocks per Gibbs round (1, 2, 4 or 8)
-void launch_walk(const WalkSub* d_subs, int n_subs, const WalkParams& prm, int nb, int tile_S, cudaStream_t st, int* launches);
+size_t walk_smem_bytes(int nb, int tile_S, bool cluster);
+// launches k_walk<nb> with one CTA -- or one cluster of `cluster` CTAs (2, 4, 8; nb must be 8) -- per subgroup;
+// nb = warps per CTA = 32-draw blocks a CTA adds to a Gibbs round (1, 2, 4 or 8)
+void launch_walk(const WalkSub* d_subs, int n_subs, const WalkParams& prm, int nb, int tile_S, int cluster, cudaStream_t st,
+                 int* launches);
 
 }  // namespace rambl

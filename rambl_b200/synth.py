@@ -379,7 +379,8 @@ def config_workload(idx: int, seed: int = 0, scale: float = 1.0) -> List[Subgrou
         return [config2_subgroup(seed * 100003 + k) for k in range(n)]
     if idx == 3:  # one deep subgroup, 1M 150bp reads, 50 strains (down-sampled to -D like StrainCall)
         return [make_subgroup(int(1000000 * scale), 150, 50, divergence=(0.01, 0.03), seed=seed)]
-    if idx == 4:  # 250bp MiSeq-like reads, indel-rich strains with homopolymer errors
-        return [make_subgroup(int(5000 * scale), 250, 4, indel_err=0.004, indel_frac=0.4,
+    if idx == 4:  # 250bp MiSeq-like reads, indel-rich strains (homopolymer-biased indels); see tools/ref_config4.py for what
+        # the reference does when the READS carry indel errors as well (it does not finish)
+        return [make_subgroup(int(5000 * scale), 250, 4, indel_err=0.0, indel_frac=0.4,
                               homopolymer_bias=True, seed=seed)]
     raise ValueError(idx)

@@ -251,10 +251,16 @@ def test_device_walk_equals_level_synchronous_path():
             b = _solve(sgs)
             texts["walk/%d" % nb] = [(b.status(i), b.strains_text(i)) for i in range(len(sgs))]
             assert b.stats()["dpm_launches"] == 1
+        assert L.rambl_set_walk_blocks(0) == api.RAMBL_OK
+        for ctas in (1, 2, 4, 8):  # a thread-block cluster per subgroup: the extra CTAs join the Gibbs chains
+            assert L.rambl_set_walk_cluster(ctas) == api.RAMBL_OK
+            b = _solve(sgs)
+            texts["cluster/%d" % ctas] = [(b.status(i), b.strains_text(i)) for i in range(len(sgs))]
     finally:
         L.rambl_set_walk_mode(1)
         L.rambl_set_walk_blocks(0)
-    assert L.rambl_set_walk_blocks(3) == api.RAMBL_ERR_INVALID
+        L.rambl_set_walk_cluster(0)
+    assert L.rambl_set_walk_blocks(3) == api.RAMBL_ERR_INVALID and L.rambl_set_walk_cluster(3) == api.RAMBL_ERR_INVALID
     for k in texts:
         for i in range(len(sgs)):
             assert texts[k][i] == texts["level-synchronous"][i], (k, i)

@@ -21,6 +21,16 @@ CASES = {
     "config2_sub0": dict(n_reads=5000, read_len=150, n_strains=2, seed=0),
     "config2_sub3": dict(n_reads=5000, read_len=150, n_strains=5, seed=3),
     "config2_sub4": dict(n_reads=5000, read_len=150, n_strains=6, seed=4),
+    # configs[3] ("one deep subgroup, 1M 150bp reads, 50 strains") at a tenth of the reads: StrainCall's -D 800 down-sampling
+    # (rho = 800 / depth) leaves the same ~8 200 reads at any raw depth above 800, so the subgroup that reaches the graph
+    # is of the size of the 1M case
+    # configs[4] ("250bp MiSeq-like reads with indel-rich strains (homopolymer errors) stressing wide POA graphs") at full
+    # size with the indels in the STRAINS: the largest form the reference finishes (tools/ref_config4.py: with read-level
+    # indel errors at >= 0.0005 per base it is killed -- segfault or out of memory -- from 500 reads up) ...
+    "config4_full": dict(n_reads=5000, read_len=250, n_strains=4, indel_err=0.0, indel_frac=0.4, homopolymer_bias=True, seed=0),
+    # ... and with read-level homopolymer indel errors at the largest size the reference finishes
+    "config4_1000_ie001": dict(n_reads=1000, read_len=250, n_strains=4, indel_err=0.001, indel_frac=0.4, homopolymer_bias=True, seed=0),
+    "config3_100k": dict(n_reads=100000, read_len=150, n_strains=50, divergence=(0.01, 0.03), seed=0),
 }
 
 
