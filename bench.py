@@ -325,7 +325,7 @@ def poa_block(api):
         probs.extend(b.msa_problems())
         b.close()
     n_distinct = len(probs)
-    while len(probs) < 4000 and n_distinct:
+    while len(probs) < 60000 and n_distinct:  # ~ the alignment problems of 500 such subgroups in one batch
         probs.extend(probs[:n_distinct])
     if not probs:
         return None

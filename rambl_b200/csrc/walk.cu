@@ -697,32 +697,54 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
             __syncwarp();
             if (fail < 0)
             {
-                // slots: the first surviving child of a parent takes the parent's slot, the others copy it
+                // slots: the first surviving child of a parent takes the parent's slot, the others copy it.  The children
+                // of a parent are consecutive, so "first" is "differs from the child before"; the others pop the free stack
+                // in child order (their rank among the non-first children).
                 for (int i = lane; i < n_keep; i += 32) ws.parent_used[i] = 0;
                 __syncwarp();
-                if (lane == 0)
+                int n_extra = 0, p_carry = -1;
+                for (int k0 = 0; k0 < K; k0 += 32)
                 {
-                    int no = 0;
-                    for (int k = 0; k < K; ++k)
+                    const int k = k0 + lane;
+                    const int p = k < K ? nx[k].pad : -2;
+                    int p_before = __shfl_up_sync(full, p, 1);
+                    if (lane == 0) p_before = p_carry;
+                    const bool first = k < K && p != p_before, extra = k < K && !first;
+                    const unsigned eb = __ballot_sync(full, extra);
+                    if (k < K)
                     {
-                        const int p = nx[k].pad;
-                        const int pslot = cs[ws.idx[p]].slot;
-                        if (!ws.parent_used[p]) { ws.parent_used[p] = 1; nx[k].slot = pslot; }
+                        const int pslot = ws.slot[ws.idx[p]];
+                        if (first) { ws.parent_used[p] = 1; nx[k].slot = pslot; }
                         else
                         {
-                            if (free_top == 0) { fail = WALK_OUT_OF_SLOTS; break; }
-                            const int dst = free_slots[--free_top];
-                            ops[no++] = make_int2(pslot, dst);
-                            nx[k].slot = dst;
+                            const int rank = n_extra + __popc(eb & lt);
+                            if (rank >= free_top) fail = WALK_OUT_OF_SLOTS;
+                            else
+                            {
+                                const int dst = free_slots[free_top - 1 - rank];
+                                ops[rank] = make_int2(pslot, dst);
+                                nx[k].slot = dst;
+                            }
                         }
                     }
-                    if (fail < 0)
-                        for (int i = 0; i < n_keep; ++i)
-                            if (!ws.parent_used[i]) free_slots[free_top++] = cs[ws.idx[i]].slot;
-                    ws.v[V_NOPS] = no;
-                    ws.v[V_FREE] = free_top;
+                    n_extra += __popc(eb);
+                    p_carry = __shfl_sync(full, p, 31);
                 }
-                fail = __shfl_sync(full, fail, 0);
+                if (__any_sync(full, fail >= 0)) fail = WALK_OUT_OF_SLOTS;
+                __syncwarp();
+                if (fail < 0)
+                {
+                    free_top -= n_extra;
+                    for (int i0 = 0; i0 < n_keep; i0 += 32)
+                    {   // parents without a surviving child give their slot back
+                        const int i = i0 + lane;
+                        const bool unused = i < n_keep && !ws.parent_used[i];
+                        const unsigned ub = __ballot_sync(full, unused);
+                        if (unused) free_slots[free_top + __popc(ub & lt)] = ws.slot[ws.idx[i]];
+                        free_top += __popc(ub);
+                    }
+                    if (lane == 0) { ws.v[V_NOPS] = n_extra; ws.v[V_FREE] = free_top; }
+                }
             }
             if (lane == 0)
             {
