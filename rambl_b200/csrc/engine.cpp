@@ -243,7 +243,7 @@ struct Engine
     DevBuf<InheritOp> d_ops;
     DevBuf<unsigned long long> d_counters;
     DevBuf<double> ll_arena, sub_arena;
-    DevBuf<char> char_arena;
+    DevBuf<char> char_arena, pool_arena;
     long long w_total = 0, max_stride = 0;
     std::vector<cudaEvent_t> gibbs_events;  // pairs, resolved after the last step
 
@@ -329,13 +329,15 @@ struct Engine
         {
             n_ll += (size_t)kInitialSlots * s.R;
             n_sub += (size_t)kInitialSlots * 36;
-            n_ch += ((s.g->label_chars.size() + 15) & ~(size_t)15) + ((s.g->pool_chars.size() + 15) & ~(size_t)15);
+            n_ch += (s.g->label_chars.size() + 15) & ~(size_t)15;
         }
         ll_arena.reserve(std::max<size_t>(n_ll, 1));
         sub_arena.reserve(std::max<size_t>(n_sub, 1));
         char_arena.reserve(std::max<size_t>(n_ch, 16));
         RAMBL_CUDA(cudaMemsetAsync(ll_arena.p, 0, sizeof(double) * n_ll, st));
         launch_init_models(sub_arena.p, (int)(n_sub / 36), e, st, &stats.launches);
+        // node labels now; the read-pool strings only for the subgroups the level-synchronous path ends up solving
+        // (upload_pool_chars) -- the device walk has them in its own level tables
         std::vector<char> host_chars(std::max<size_t>(n_ch, 16), 0);
         size_t o_ll = 0, o_sub = 0, o_ch = 0;
         for (Sub& s : subs)
@@ -347,9 +349,7 @@ struct Engine
             s.d_label = char_arena.p + o_ch;
             if (!s.g->label_chars.empty()) memcpy(&host_chars[o_ch], s.g->label_chars.data(), s.g->label_chars.size());
             o_ch += (s.g->label_chars.size() + 15) & ~(size_t)15;
-            s.d_pool = char_arena.p + o_ch;
-            if (!s.g->pool_chars.empty()) memcpy(&host_chars[o_ch], s.g->pool_chars.data(), s.g->pool_chars.size());
-            o_ch += (s.g->pool_chars.size() + 15) & ~(size_t)15;
+            s.d_pool = nullptr;
         }
         RAMBL_CUDA(cudaMemcpyAsync(char_arena.p, host_chars.data(), host_chars.size(), cudaMemcpyHostToDevice, st));
         RAMBL_CUDA(cudaStreamSynchronize(st));  // host_chars goes out of scope
@@ -360,6 +360,27 @@ struct Engine
             root.slot = take_slot(s);
             s.cands.push_back(root);
         }
+    }
+
+    // the read-pool strings of the subgroups that still have levels to walk on the level-synchronous path
+    void upload_pool_chars()
+    {
+        size_t n = 0;
+        for (const Sub& s : subs) if (!s.done && !s.d_pool) n += (s.g->pool_chars.size() + 15) & ~(size_t)15;
+        if (n == 0) return;
+        pool_arena.reserve(n);
+        std::vector<char> host(n, 0);
+        size_t o = 0;
+        for (Sub& s : subs)
+        {
+            if (s.done || s.d_pool) continue;
+            s.d_pool = pool_arena.p + o;
+            if (!s.g->pool_chars.empty()) memcpy(&host[o], s.g->pool_chars.data(), s.g->pool_chars.size());
+            o += (s.g->pool_chars.size() + 15) & ~(size_t)15;
+        }
+        RAMBL_CUDA(cudaMemcpyAsync(pool_arena.p, host.data(), n, cudaMemcpyHostToDevice, st));
+        RAMBL_CUDA(cudaStreamSynchronize(st));
+        stats.h2d_bytes += (long long)n;
     }
 
     // ---- "$": read_reassign's sort + merge_strains, NonparametricClustering.cpp:309-315,645-702 ----
@@ -847,14 +868,15 @@ struct Engine
         int reason = 0;  // why not: 1 a node on two levels, 2 "$" not alone / not last, 3 a read twice on a level, 4 entry range,
                          // 5 "^" carries reads, 6 size, 7 mate id out of range, 8 no graph
         int n_levels = 0, max_m = 0, max_D = 0;
-        bool multi = false;                  // some read-pool entry has more than one letter
+        std::vector<int> lvl_moff;           // [n_levels] -1, or the level's start in the multi-letter tables
+        long long n_ment = 0, n_mchars = 0;  // entries / letters of the levels that hold multi-letter entries
         std::vector<int> order;              // nodes in walk order (levels concatenated)
         std::vector<int> lvl_ent_off;        // [n_levels + 1]
         std::vector<unsigned char> lvl_dup;  // [n_levels] a read with several entries on the level
         long long n_ent = 0, n_chars = 0;
         // offsets into the static arena (bytes) and the scratch arena (bytes)
-        size_t o_label_off = 0, o_out_off = 0, o_out_to = 0, o_out_cover = 0, o_lvl = 0, o_dup = 0, o_rid = 0, o_cn = 0, o_soff = 0,
-               o_len = 0, o_chars = 0, o_pair_off = 0, o_pair_val = 0;
+        size_t o_label_off = 0, o_out_off = 0, o_out_to = 0, o_out_cover = 0, o_lvl = 0, o_dup = 0, o_rid = 0, o_cn = 0, o_char1 = 0, o_moff = 0,
+               o_soff = 0, o_len = 0, o_chars = 0, o_pair_off = 0, o_pair_val = 0;
         size_t d_present = 0, d_free = 0, d_cand0 = 0, d_cand1 = 0, d_trail = 0, d_W = 0, d_doff = 0, d_dent = 0, d_dmate = 0,
                d_fresh = 0, d_ab = 0, d_ops = 0, d_kid = 0, d_lut = 0, d_helper = 0, d_res = 0, d_paths = 0, d_fslot = 0, d_fab = 0;
         int trail_cap = 0;
@@ -890,8 +912,9 @@ struct Engine
         {
             if (ended) { ok = false; p.reason = 2; break; }  // something follows "$"
             if (level > g.n_nodes + 1) { ok = false; p.reason = 1; break; }  // not a DAG
-            long long m = 0, D = 0;
+            long long m = 0, D = 0, chars = 0;
             unsigned char dup = 0;
+            bool multi = false;
             nxt.clear();
             for (int u : cur)
             {
@@ -903,8 +926,8 @@ struct Engine
                         if (cn < 1 || cn > 255 || len < 1 || len > 255) { ok = false; p.reason = 4; break; }
                         if (seen_rid[rid] == level) dup = 1;  // its further entries are added after the first, in entry order
                         seen_rid[rid] = level;
-                        if (len > 1) p.multi = true;
-                        m += 1; D += cn; p.n_chars += len;
+                        if (len > 1) multi = true;
+                        m += 1; D += cn; chars += len;
                     }
                 else if (g.pool_off[1] != g.pool_off[0] || level != 0) { ok = false; p.reason = 5; }  // "^" carries no reads
                 if (!ok) break;
@@ -919,6 +942,8 @@ struct Engine
             p.n_ent += m;
             p.lvl_ent_off.push_back((int)p.n_ent);
             p.lvl_dup.push_back(dup);
+            p.lvl_moff.push_back(multi ? (int)p.n_ment : -1);
+            if (multi) { p.n_ment += m; p.n_mchars += chars; }
             p.max_m = std::max<long long>(p.max_m, m);
             p.max_D = std::max<long long>(p.max_D, D);
             if (D > 40000 * 8 || p.n_ent > 0x7fffff00LL) { ok = false; p.reason = 6; break; }
@@ -963,8 +988,11 @@ struct Engine
             put(p.o_dup, p.lvl_dup.size());
             put(p.o_rid, sizeof(unsigned) * p.n_ent);
             put(p.o_cn, (size_t)p.n_ent);
-            if (p.multi) { put(p.o_soff, sizeof(unsigned) * p.n_ent); put(p.o_len, (size_t)p.n_ent); }
-            put(p.o_chars, (size_t)p.n_chars);
+            put(p.o_char1, (size_t)p.n_ent);
+            put(p.o_moff, sizeof(int) * p.lvl_moff.size());
+            put(p.o_soff, sizeof(unsigned) * p.n_ment);
+            put(p.o_len, (size_t)p.n_ment);
+            put(p.o_chars, (size_t)p.n_mchars);
             put(p.o_pair_off, sizeof(int) * in.pair_off.size());
             put(p.o_pair_val, sizeof(int) * in.pair_val.size());
             auto scr = [&](size_t& off, size_t bytes) { off = scr_bytes; scr_bytes += up16(bytes) + 112; scr_bytes &= ~size_t(127); };
@@ -993,6 +1021,14 @@ struct Engine
             for (const WalkPlan& p : plans) if (!p.eligible) why[std::min(std::max(p.reason, 0), 8)] += 1;
             fprintf(stderr, "[rambl] device walk: %zu of %zu subgroups not eligible (reasons 1..8: %d %d %d %d %d %d %d %d)\n",
                     n - take.size(), n, why[1], why[2], why[3], why[4], why[5], why[6], why[7], why[8]);
+            int shown = 0;
+            for (size_t i = 0; i < n && shown < 4; ++i)
+                if (!plans[i].eligible)
+                {
+                    fprintf(stderr, "[rambl]   subgroup %zu: reason %d after %zu levels, %d nodes, %d reads\n", i, plans[i].reason,
+                            plans[i].lvl_ent_off.size() - 1, subs[i].g->n_nodes, subs[i].g->n_reads);
+                    ++shown;
+                }
         }
         if (take.empty()) return 0;
         // ---- fill the static tables (pinned) on the workers, one copy to the device
@@ -1020,10 +1056,12 @@ struct Engine
             memcpy(H + p.o_dup, p.lvl_dup.data(), p.lvl_dup.size());
             unsigned* rid = reinterpret_cast<unsigned*>(H + p.o_rid);
             unsigned char* cn = reinterpret_cast<unsigned char*>(H + p.o_cn);
-            unsigned* soff = p.multi ? reinterpret_cast<unsigned*>(H + p.o_soff) : nullptr;
-            unsigned char* len = p.multi ? reinterpret_cast<unsigned char*>(H + p.o_len) : nullptr;
+            char* char1 = H + p.o_char1;
+            unsigned* soff = reinterpret_cast<unsigned*>(H + p.o_soff);
+            unsigned char* len = reinterpret_cast<unsigned char*>(H + p.o_len);
             char* chars = H + p.o_chars;
-            size_t at = 0, at_c = 0;
+            memcpy(H + p.o_moff, p.lvl_moff.data(), sizeof(int) * p.lvl_moff.size());
+            size_t at = 0, at_m = 0, at_c = 0;
             std::vector<int> seen(std::max(1, g.n_reads), -1);
             size_t lvl = 0;
             for (int u : p.order)
@@ -1037,10 +1075,15 @@ struct Engine
                     seen[r0] = (int)lvl;
                     cn[at] = (unsigned char)g.pool_cn[e];
                     const int l = g.pool_str_off[e + 1] - g.pool_str_off[e];
-                    if (soff) { soff[at] = (unsigned)at_c; len[at] = (unsigned char)l; }
-                    if (l == 1) chars[at_c] = g.pool_chars[g.pool_str_off[e]];
-                    else memcpy(chars + at_c, g.pool_chars.data() + g.pool_str_off[e], (size_t)l);
-                    at_c += (size_t)l;
+                    char1[at] = g.pool_chars[g.pool_str_off[e]];
+                    if (p.lvl_moff[lvl] >= 0)
+                    {
+                        soff[at_m] = (unsigned)at_c;
+                        len[at_m] = (unsigned char)l;
+                        memcpy(chars + at_c, g.pool_chars.data() + g.pool_str_off[e], (size_t)l);
+                        at_c += (size_t)l;
+                        ++at_m;
+                    }
                 }
             }
             memcpy(H + p.o_pair_off, in.pair_off.data(), sizeof(int) * in.pair_off.size());
@@ -1073,9 +1116,11 @@ struct Engine
             w.lvl_dup = reinterpret_cast<const unsigned char*>(Dst + p.o_dup);
             w.ent_rid = reinterpret_cast<const unsigned*>(Dst + p.o_rid);
             w.ent_cn = reinterpret_cast<const unsigned char*>(Dst + p.o_cn);
-            w.ent_soff = p.multi ? reinterpret_cast<const unsigned*>(Dst + p.o_soff) : nullptr;
-            w.ent_len = p.multi ? reinterpret_cast<const unsigned char*>(Dst + p.o_len) : nullptr;
-            w.ent_chars = Dst + p.o_chars;
+            w.ent_char1 = Dst + p.o_char1;
+            w.lvl_moff = reinterpret_cast<const int*>(Dst + p.o_moff);
+            w.m_soff = reinterpret_cast<const unsigned*>(Dst + p.o_soff);
+            w.m_len = reinterpret_cast<const unsigned char*>(Dst + p.o_len);
+            w.m_chars = Dst + p.o_chars;
             w.pair_off = reinterpret_cast<const int*>(Dst + p.o_pair_off);
             w.pair_val = reinterpret_cast<const int*>(Dst + p.o_pair_val);
             w.R = s.R;
@@ -1288,6 +1333,7 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
             if (getenv("RAMBL_TRACE")) fprintf(stderr, "[rambl] device walk solved %d of %zu subgroups, until %.1f ms\n", taken, E.subs.size(), since(w0));
         }
     }
+    E.upload_pool_chars();
     double trace[4] = {0, 0, 0, 0};
     auto for_subs = [&](const std::function<void(size_t)>& fn) {
         if (E.workers) E.workers->run(E.subs.size(), fn);

@@ -138,9 +138,11 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
     const unsigned char* const lvl_dup = w->lvl_dup;
     const unsigned* const ent_rid = w->ent_rid;
     const unsigned char* const ent_cn = w->ent_cn;
-    const unsigned* const ent_soff = w->ent_soff;
-    const unsigned char* const ent_len = w->ent_len;
-    const char* const ent_chars = w->ent_chars;
+    const char* const ent_char1 = w->ent_char1;
+    const int* const lvl_moff = w->lvl_moff;
+    const unsigned* const m_soff = w->m_soff;
+    const unsigned char* const m_len = w->m_len;
+    const char* const m_chars = w->m_chars;
     const int* const pair_off = w->pair_off;
     const int* const pair_val = w->pair_val;
     const int R = w->R;
@@ -230,6 +232,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
         if (level == n_levels - 1) break;  // "$": the host closes the result (sort + merge_strains)
         if (S == 0) break;
         const int e0 = lvl_ent_off[level], m = lvl_ent_off[level + 1] - e0;
+        const int mo = lvl_moff[level];  // -1: every entry of the level is one letter; else its entries' (offset, length) table
         const int mode = (m > 0) ? (ws.v[V_BRANCH] ? MODE_GIBBS : MODE_HARD) : MODE_NONE;
         if (S > WALK_SMAX)
         {
@@ -349,8 +352,8 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                 const unsigned er = ent_rid[e0 + r];
                 if (er >> 31) continue;
                 const int rid = (int)er;
-                const char* rs = ent_chars + (ent_soff ? ent_soff[e0 + r] : (unsigned)(e0 + r));
-                const int rl = ent_len ? (int)ent_len[e0 + r] : 1;
+                const char* rs = mo >= 0 ? m_chars + m_soff[mo + r] : ent_char1 + e0 + r;
+                const int rl = mo >= 0 ? (int)m_len[mo + r] : 1;
                 for (int s0 = 0; s0 < S; s0 += 4)
                 {
                     double dv[4], old[4];
@@ -379,8 +382,8 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                     {
                         const unsigned er = ent_rid[e0 + r];
                         if (!(er >> 31)) continue;
-                        const char* rs = ent_chars + (ent_soff ? ent_soff[e0 + r] : (unsigned)(e0 + r));
-                        row[er & 0x7fffffffu] += entry_term(st, r, rs, ent_len ? (int)ent_len[e0 + r] : 1);
+                        const char* rs = mo >= 0 ? m_chars + m_soff[mo + r] : ent_char1 + e0 + r;
+                        row[er & 0x7fffffffu] += entry_term(st, r, rs, mo >= 0 ? (int)m_len[mo + r] : 1);
                     }
                 }
             }
@@ -411,8 +414,8 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                 }
                 if (mode == MODE_GIBBS)
                 {
-                    const int rl = ent_len ? (int)ent_len[e0 + r] : 1;
-                    codes[d] = (rl == 1) ? letter_code(ent_chars[ent_soff ? ent_soff[e0 + r] : (unsigned)(e0 + r)]) : 7;
+                    const int rl = mo >= 0 ? (int)m_len[mo + r] : 1;
+                    codes[d] = (rl == 1) ? letter_code(mo >= 0 ? m_chars[m_soff[mo + r]] : ent_char1[e0 + r]) : 7;
                 }
             }
             // the Gibbs chain reads its tiles through the async proxy (bulk copies): order the generic-proxy stores
@@ -443,8 +446,8 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                         const double p = a_s * wt[weight_index(d, s, S)] / norms[d];
                         acc[0] += p;
                         const int r = draw_entry[d];
-                        const char* rs = ent_chars + (ent_soff ? ent_soff[e0 + r] : (unsigned)(e0 + r));
-                        const int rl = ent_len ? (int)ent_len[e0 + r] : 1;
+                        const char* rs = mo >= 0 ? m_chars + m_soff[mo + r] : ent_char1 + e0 + r;
+                        const int rl = mo >= 0 ? (int)m_len[mo + r] : 1;
                         if (rl == 1)
                         {
                             const int b = letter_code(rs[0]);

@@ -66,9 +66,11 @@ struct WalkSub
     const unsigned char* lvl_dup;   // [n_levels] some read has more than one entry on the level
     const unsigned* ent_rid;        // [entries] unique read id; bit 31: a further entry of a read already listed on this level
     const unsigned char* ent_cn;    // [entries] copies
-    const unsigned* ent_soff;       // [entries] offset of the entry's letters in ent_chars, or null: offset == index
-    const unsigned char* ent_len;   // [entries] letters, or null: 1
-    const char* ent_chars;
+    const char* ent_char1;          // [entries] the entry's letter (levels whose entries are all one letter: nearly all)
+    const int* lvl_moff;            // [n_levels] -1, or where the level's entries start in m_soff / m_len (collapsed nodes)
+    const unsigned* m_soff;         // offset of an entry's letters in m_chars
+    const unsigned char* m_len;     // its length
+    const char* m_chars;
     const int* pair_off;            // ReadPairs as CSR over unique reads: one mate id or -1 per copy
     const int* pair_val;
     int R;                          // unique reads == row stride of ll

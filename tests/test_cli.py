@@ -175,3 +175,29 @@ def test_cli_equals_library_path(tmp_path):
     b.build_graphs()
     b.infer()
     assert out == b.fasta(0, "gx", 1, len(gene), 0.02)
+
+
+def test_config3_reads_through_the_cli_glue_equal_the_golden_input(tmp_path):
+    """CPU: BASELINE configs[3] at a tenth of its raw reads (100 000 x 150 bp of 50 strains, ~9 700x deep) through the
+    drop-in CLI's window / filter / -D 800 down-sampling / de-duplication glue gives exactly the subgroup the unmodified
+    reference was run on for tests/golden/full_config3_100k.json.gz (the GPU suite then checks the strains).  The depth
+    cap makes the subgroup that reaches the graph independent of the raw depth, so this is the 1M-read case in all but
+    the time the samtools stand-in needs to read the SAM text (tools/config3_glue.py runs the full million)."""
+    from helpers import load_golden_gz
+    path = os.path.join(ROOT, "tests", "golden", "full_config3_100k.json.gz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/full_config3_100k.json.gz not generated yet")
+    case = load_golden_gz("full_config3_100k.json.gz")
+    spec = dict(case["spec"])
+    spec["divergence"] = tuple(spec["divergence"])
+    gene, raw, _ = synth.simulate_raw_reads(**spec)
+    fa, sam = synth.write_cli_fixture(str(tmp_path), "deep", gene, raw)
+    dump = os.path.join(str(tmp_path), "dump.txt")
+    code, _, err = run_cli(CLI, ["-r", "deep:1-%d" % len(gene), "-w", "5000", "-q", "0", "-D", "800", "-I", "13", "-l", "20",
+                                 fa, sam, "--dump-inputs", dump], str(tmp_path))
+    assert code == 0, err
+    (w,) = parse_dump(dump)
+    inp = case["input"]
+    assert sum(w["cn"]) < 0.1 * len(raw)  # the depth cap was active
+    assert (w["gene"], w["pos"], w["cigar"], w["seq"], w["cn"]) == (inp["gene"], inp["pos"], inp["cigar"], inp["seq"], inp["cn"])
+    assert [m for ms in w["mates"] for m in ms] == inp["pair_val"]

@@ -9,7 +9,8 @@ import pytest
 from helpers import ROOT, load_golden_gz
 from rambl_b200 import synth
 
-CASES = ["config0_seed0", "config1_seed0", "config2_sub0", "config2_sub3", "config2_sub4"]
+CASES = ["config0_seed0", "config1_seed0", "config2_sub0", "config2_sub3", "config2_sub4", "config4_full",
+               "config4_1000_ie001", "config3_100k"]
 
 
 @pytest.mark.parametrize("name", CASES)

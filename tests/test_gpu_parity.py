@@ -326,13 +326,17 @@ def test_matched_sample_set_of_the_bench_matches_reference():
         assert compare_strains(want, got) == [], i
 
 
-FULL_GOLDEN = ["config0_seed0", "config1_seed0", "config2_sub0", "config2_sub3", "config2_sub4"]
+FULL_GOLDEN = ["config0_seed0", "config1_seed0", "config2_sub0", "config2_sub3", "config2_sub4", "config4_full",
+               "config4_1000_ie001", "config3_100k"]
 
 
 @pytest.mark.parametrize("name", FULL_GOLDEN)
 def test_full_size_matches_golden_reference(name):
-    """BASELINE configs[0], configs[1] (the single-chain bench block) and whole-gene subgroups of configs[2] (the bench
-    workload) at FULL size against what the unmodified reference produced for the same inputs
+    """BASELINE configs[0], configs[1] (the single-chain bench block), whole-gene subgroups of configs[2] (the bench
+    workload), configs[4] at full size (5 000 x 250 bp reads, indel-rich strains: wide graphs, the insertion alignment
+    on the device) and with read-level homopolymer indel errors at the largest size the reference finishes, and
+    configs[3] (100k raw reads of 50 strains through the depth-800 down-sampling) against what the unmodified reference
+    produced for the same inputs
     (tests/golden/full_*.json.gz, generated by tools/make_golden_full.py; the reference needs 1-13 minutes per case):
     graph (node dump and output_edge text by hash), strain paths, order, consensus, abundances, substitution tables
     and every per-read log-likelihood."""
