@@ -52,6 +52,9 @@ typedef struct rambl_stats
     float dpm_kernel_ms;      /* CUDA-event time of the device-resident strain walk (one kernel, one CTA per subgroup) */
     int32_t dpm_launches;
     int64_t dpm_alg_bytes;    /* its algorithmic bytes: Gibbs bytes + 16 B per log-likelihood update + 16 B per weight */
+    int32_t offtable_levels;  /* graph levels where a one-letter strain label can meet a multi-letter read string: the reference
+                               * then counts substitution keys outside its 6x6 table; this library does not (0 on every test input) */
+    int32_t reserved;
 } rambl_stats;
 
 const char* rambl_last_error(void);
@@ -146,6 +149,11 @@ int rambl_batch_finish_graphs_with_rows(rambl_batch* b, const char* rows_text);
  * subgroups whose candidate set outgrew the kernels (more than 256 live strains, which needs
  * degenerate abundances) get RAMBL_ERR_CAPACITY; the call itself still returns RAMBL_OK. */
 int rambl_batch_infer(rambl_batch* b, int32_t n, float e, float tau, float diff, int32_t do_assign, int32_t keep_loglik);
+
+/* rambl_batch_build_graphs + rambl_batch_infer in one call that overlaps them: the batch is dealt into chunks and the
+ * host builds the graphs of one chunk while the device searches the strains of the previous one (two CUDA streams).
+ * Same results as the two calls (subgroups never interact); what StrainCall's main() loop is to the CLI. */
+int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff, int32_t do_assign, int32_t keep_loglik);
 
 /* ---- results */
 int32_t rambl_batch_num_subgroups(const rambl_batch* b);

@@ -40,7 +40,8 @@ class Stats(C.Structure):
                 ("msa_kernel_ms", C.c_float), ("infer_gpu_ms", C.c_float), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("gibbs_kernel_ms", C.c_float), ("gibbs_launches", C.c_int32),
                 ("gibbs_alg_bytes", C.c_int64), ("gibbs_rounds", C.c_int64), ("gibbs_passes", C.c_int64),
-                ("dpm_kernel_ms", C.c_float), ("dpm_launches", C.c_int32), ("dpm_alg_bytes", C.c_int64)]
+                ("dpm_kernel_ms", C.c_float), ("dpm_launches", C.c_int32), ("dpm_alg_bytes", C.c_int64),
+                ("offtable_levels", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -76,6 +77,7 @@ SYMBOLS = {
     "rambl_batch_msa_problems_text": (C.c_void_p, [C.c_void_p]),
     "rambl_batch_finish_graphs_with_rows": (C.c_int, [C.c_void_p, C.c_char_p]),
     "rambl_batch_infer": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32]),
+    "rambl_batch_solve": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32]),
     "rambl_batch_num_subgroups": (C.c_int32, [C.c_void_p]),
     "rambl_batch_num_nodes": (C.c_int32, [C.c_void_p, C.c_int32]),
     "rambl_batch_graph_text": (C.c_void_p, [C.c_void_p, C.c_int32, C.c_int32]),
@@ -311,6 +313,11 @@ class StrainCallBatch:
     def infer(self, n: int = 5000, e: float = 0.01, tau: float = 0.02, diff: float = 0.01, assign: bool = True,
               keep_loglik: bool = False):
         _check(lib().rambl_batch_infer(self._h, n, e, tau, diff, int(assign), int(keep_loglik)))
+
+    def solve(self, n: int = 5000, e: float = 0.01, tau: float = 0.02, diff: float = 0.01, assign: bool = True,
+              keep_loglik: bool = False):
+        """build_graphs() + infer() as one call that overlaps host graph construction with the device strain search."""
+        _check(lib().rambl_batch_solve(self._h, n, e, tau, diff, int(assign), int(keep_loglik)))
 
     # results ------------------------------------------------------------------------------------
     def num_subgroups(self) -> int:

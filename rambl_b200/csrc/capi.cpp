@@ -8,6 +8,7 @@
 #include <sstream>
 #include <thread>
 #include <atomic>
+#include <mutex>
 
 #include "dpm.cuh"
 #include "engine.hpp"
@@ -570,7 +571,133 @@ int rambl_batch_infer(rambl_batch* b, int32_t n, float e, float tau, float diff,
         b->stats.dpm_kernel_ms += es.walk_ms;
         b->stats.dpm_launches += es.walk_launches;
         b->stats.dpm_alg_bytes += es.walk_bytes;
+        b->stats.offtable_levels += es.offtable_levels;
         b->last = prm;
+    });
+}
+
+// rambl_batch_build_graphs + rambl_batch_infer as ONE call that overlaps them: the subgroups are dealt into chunks,
+// two driver threads (each with its own CUDA stream) take chunks in order, so the host builds the graphs of one chunk
+// while the device walks the previous one.  Results are what the two separate calls give (subgroups never interact).
+int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff, int32_t do_assign, int32_t keep_loglik)
+{
+    return guarded([&] {
+        if (!b) throw Error(RAMBL_ERR_INVALID, "null batch");
+        require_device();
+        const size_t N = b->subs.size();
+        bool fresh = b->threaded_upto == 0 && b->msa.problems() == 0;
+        for (auto& sp : b->subs) fresh = fresh && !sp->built;
+        const size_t n_chunks = N >= 96 ? 4 : (N >= 16 ? 2 : 1);
+        if (!fresh || n_chunks == 1)
+        {   // nothing to overlap (or a batch that is partly built already): the two calls, one after the other
+            int rc = rambl_batch_build_graphs(b);
+            if (rc != RAMBL_OK) throw Error(rc, g_error);
+            rc = rambl_batch_infer(b, n, e, tau, diff, do_assign, keep_loglik);
+            if (rc != RAMBL_OK) throw Error(rc, g_error);
+            return;
+        }
+        InferParams prm;
+        prm.n = n; prm.e = e; prm.tau = tau; prm.diff = diff; prm.assign = do_assign != 0; prm.keep_loglik = keep_loglik != 0;
+        int device = 0;
+        RAMBL_CUDA(cudaGetDevice(&device));
+        std::atomic<size_t> next(0);
+        std::mutex mu;
+        std::string what;
+        int code = RAMBL_OK;
+        const auto w0 = std::chrono::steady_clock::now();
+        auto drive = [&] {
+            cudaStream_t st = nullptr;
+            try
+            {
+                RAMBL_CUDA(cudaSetDevice(device));
+                RAMBL_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+                for (;;)
+                {
+                    const size_t c = next.fetch_add(1);
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        if (c >= n_chunks || code != RAMBL_OK) break;
+                    }
+                    const size_t lo = N * c / n_chunks, hi = N * (c + 1) / n_chunks;
+                    // ---- graphs of this chunk: splice, align the insertion levels on the device, finish
+                    std::vector<MsaBatch> local(hi - lo);
+                    parallel_for(lo, hi, [&](size_t i) {
+                        Subgroup& s = *b->subs[i];
+                        s.builder.reset(new GraphBuilder);
+                        s.builder->thread(s.gene, s.reads, local[i - lo]);
+                    });
+                    MsaBatch msa;
+                    for (size_t i = lo; i < hi; ++i)
+                    {
+                        const MsaBatch& m = local[i - lo];
+                        b->subs[i]->builder->rebase_problems(msa.problems());
+                        for (int p = 0; p < m.problems(); ++p)
+                        {
+                            for (int q = m.prob_seq_off[p]; q < m.prob_seq_off[p + 1]; ++q)
+                                msa.add_sequence(m.chars.data() + m.seq_off[q], m.seq_off[q + 1] - m.seq_off[q]);
+                            msa.end_problem();
+                        }
+                    }
+                    MsaResult rows;
+                    msa_sp_align_batch(msa, rows, st);
+                    parallel_for(lo, hi, [&](size_t i) {
+                        Subgroup& s = *b->subs[i];
+                        s.builder->finish(rows, s.graph);
+                        s.builder.reset();
+                        s.input.graph = &s.graph;
+                        s.built = true;
+                    });
+                    // ---- strain search of this chunk
+                    std::vector<SubgroupInput> in;
+                    for (size_t i = lo; i < hi; ++i) in.push_back(b->subs[i]->input);
+                    std::vector<SubgroupResult> out;
+                    EngineStats es;
+                    infer_batch(in, prm, out, es, st);
+                    std::lock_guard<std::mutex> lk(mu);
+                    for (size_t i = lo; i < hi; ++i) { b->subs[i]->result = std::move(out[i - lo]); b->subs[i]->inferred = true; }
+                    b->stats.gpu_launches += rows.launches + es.launches;
+                    b->stats.msa_dp_cells += (int64_t)rows.dp_cells;
+                    b->stats.msa_problems += msa.problems();
+                    b->stats.msa_kernel_ms += rows.kernel_ms;
+                    b->stats.h2d_bytes += (int64_t)(msa.chars.size() + 4 * (msa.seq_off.size() + msa.prob_seq_off.size())) + es.h2d_bytes;
+                    b->stats.d2h_bytes += (int64_t)rows.rows.size() + es.d2h_bytes;
+                    b->stats.level_steps += es.level_steps;
+                    b->stats.draws += es.draws;
+                    b->stats.loglik_updates += es.loglik_updates;
+                    b->stats.infer_gpu_ms += es.gpu_ms;
+                    b->stats.gibbs_kernel_ms += es.gibbs_ms;
+                    b->stats.gibbs_launches += es.gibbs_launches;
+                    b->stats.gibbs_alg_bytes += es.gibbs_bytes;
+                    b->stats.gibbs_rounds += es.gibbs_rounds;
+                    b->stats.gibbs_passes += es.gibbs_passes;
+                    b->stats.dpm_kernel_ms += es.walk_ms;
+                    b->stats.dpm_launches += es.walk_launches;
+                    b->stats.dpm_alg_bytes += es.walk_bytes;
+                    b->stats.offtable_levels += es.offtable_levels;
+                }
+            }
+            catch (const Error& er)
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (code == RAMBL_OK) { code = er.code; what = er.what(); }
+            }
+            catch (const std::exception& er)
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (code == RAMBL_OK) { code = RAMBL_ERR_INVALID; what = er.what(); }
+            }
+            if (st) cudaStreamDestroy(st);
+        };
+        std::thread second(drive);
+        drive();
+        second.join();
+        b->threaded_upto = N;
+        b->msa = MsaBatch();
+        b->last = prm;
+        if (getenv("RAMBL_TRACE"))
+            fprintf(stderr, "[rambl] rambl_batch_solve: %zu subgroups in %zu chunks, %.1f ms\n", N, n_chunks,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count());
+        if (code != RAMBL_OK) throw Error(code, what);
     });
 }
 

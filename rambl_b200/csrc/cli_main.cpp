@@ -517,12 +517,10 @@ int main(int argc, char** argv)
     }
     if (!kept.empty())
     {
-        if (rambl_batch_build_graphs(b) != RAMBL_OK) { std::cerr << "StrainCall: " << rambl_last_error() << std::endl; return 1; }
-        if (!o.plot_graph && rambl_batch_infer(b, 5000, o.error_rate, o.tau, o.diff_rate, 1, 0) != RAMBL_OK)
-        {
-            std::cerr << "StrainCall: " << rambl_last_error() << std::endl;
-            return 1;
-        }
+        // graphs only for -G; else graphs and strains in one call (construction of one chunk of windows overlaps the
+        // strain search of the previous one)
+        const int rc = o.plot_graph ? rambl_batch_build_graphs(b) : rambl_batch_solve(b, 5000, o.error_rate, o.tau, o.diff_rate, 1, 0);
+        if (rc != RAMBL_OK) { std::cerr << "StrainCall: " << rambl_last_error() << std::endl; return 1; }
     }
     for (size_t i = 0; i < kept.size(); ++i)
     {

@@ -94,6 +94,7 @@ struct Sub
     std::vector<std::pair<int, int>> ops;  // (src slot, dst slot) copies to run before the next level
     int local_launches = 0;
     long long step_updates = 0, step_draws = 0;
+    int side = -1;  // solved by the side batch (level-synchronous path, own stream and thread): index there
     // result
     bool have_result = false;
     std::vector<Cand> result;
@@ -865,11 +866,14 @@ struct Engine
     struct WalkPlan  // host side of one subgroup's tables
     {
         bool eligible = false;
+        bool handoff = false;            // "$" shares a level with other nodes: the walk stops before that level and the
+        std::vector<int> handoff_cur;    // level-synchronous path goes on from there (these are the level's nodes)
         int reason = 0;  // why not: 1 a node on two levels, 2 "$" not alone / not last, 3 a read twice on a level, 4 entry range,
                          // 5 "^" carries reads, 6 size, 7 mate id out of range, 8 no graph
         int n_levels = 0, max_m = 0, max_D = 0;
         std::vector<int> lvl_moff;           // [n_levels] -1, or the level's start in the multi-letter tables
         long long n_ment = 0, n_mchars = 0;  // entries / letters of the levels that hold multi-letter entries
+        int mixed_levels = 0;                // levels with a multi-letter read string next to a one-letter node
         std::vector<int> order;              // nodes in walk order (levels concatenated)
         std::vector<int> lvl_ent_off;        // [n_levels + 1]
         std::vector<unsigned char> lvl_dup;  // [n_levels] a read with several entries on the level
@@ -886,6 +890,22 @@ struct Engine
     DevBuf<char> d_static, d_scratch;
     DevBuf<WalkSub> d_walk;
     DevBuf<WalkResult> d_walk_res;
+    // Subgroups the walk cannot take are solved by the level-synchronous path WHILE the walk kernel runs: a second call
+    // of infer_batch on its own stream and host thread (their per-level launches slip into the SMs the walk's waves
+    // leave free, instead of adding a whole chain's latency after it)
+    std::vector<SubgroupInput> side_in;
+    std::vector<SubgroupResult> side_out;
+    EngineStats side_stats;
+    std::thread side_thread;
+    std::exception_ptr side_error;
+    cudaStream_t side_stream = nullptr;
+    void join_side()
+    {
+        if (side_thread.joinable()) side_thread.join();
+        if (side_stream) { cudaStreamDestroy(side_stream); side_stream = nullptr; }
+        if (side_error) { std::exception_ptr e2 = side_error; side_error = nullptr; std::rethrow_exception(e2); }
+    }
+    ~Engine() { if (side_thread.joinable()) side_thread.join(); if (side_stream) cudaStreamDestroy(side_stream); }
     DevBuf<int> d_final_slot;
     DevBuf<double> d_final_ab;
 
@@ -912,14 +932,24 @@ struct Engine
         {
             if (ended) { ok = false; p.reason = 2; break; }  // something follows "$"
             if (level > g.n_nodes + 1) { ok = false; p.reason = 1; break; }  // not a DAG
+            if (cur.size() > 1 && std::find(cur.begin(), cur.end(), g.end_node) != cur.end())
+            {   // "$" next to other nodes (a graph that is not strictly levelled): the device walks up to here
+                p.handoff = true;
+                p.handoff_cur = cur;
+                ended = true;
+                level += 1;
+                break;
+            }
             long long m = 0, D = 0, chars = 0;
             unsigned char dup = 0;
-            bool multi = false;
+            bool multi = false, single_node = false;
             nxt.clear();
             for (int u : cur)
             {
-                if (u == g.end_node) { if (cur.size() != 1) { ok = false; p.reason = 2; } ended = true; }
+                if (u == g.end_node) ended = true;
                 else if (u != 0)
+                {
+                    if (g.label_off[u + 1] - g.label_off[u] == 1) single_node = true;
                     for (int e = g.pool_off[u]; e < g.pool_off[u + 1]; ++e)
                     {
                         const int rid = g.pool_rid[e], cn = g.pool_cn[e], len = g.pool_str_off[e + 1] - g.pool_str_off[e];
@@ -929,6 +959,7 @@ struct Engine
                         if (len > 1) multi = true;
                         m += 1; D += cn; chars += len;
                     }
+                }
                 else if (g.pool_off[1] != g.pool_off[0] || level != 0) { ok = false; p.reason = 5; }  // "^" carries no reads
                 if (!ok) break;
                 p.order.push_back(u);
@@ -944,6 +975,7 @@ struct Engine
             p.lvl_dup.push_back(dup);
             p.lvl_moff.push_back(multi ? (int)p.n_ment : -1);
             if (multi) { p.n_ment += m; p.n_mchars += chars; }
+            if (multi && single_node) p.mixed_levels += 1;
             p.max_m = std::max<long long>(p.max_m, m);
             p.max_D = std::max<long long>(p.max_D, D);
             if (D > 40000 * 8 || p.n_ent > 0x7fffff00LL) { ok = false; p.reason = 6; break; }
@@ -969,6 +1001,7 @@ struct Engine
             else for (size_t i = 0; i < n; ++i) fn(i);
         };
         each([&](size_t i) { plan_walk(i); });
+        for (const WalkPlan& p : plans) stats.offtable_levels += p.mixed_levels;
         std::vector<int> take;
         size_t stat_bytes = 0, scr_bytes = 0;
         for (size_t i = 0; i < n; ++i)
@@ -1031,6 +1064,29 @@ struct Engine
                 }
         }
         if (take.empty()) return 0;
+        if (take.size() < n)
+        {   // the rest: level-synchronous, concurrently (see side_in)
+            for (size_t i = 0; i < n; ++i)
+                if (!plans[i].eligible)
+                {
+                    subs[i].side = (int)side_in.size();
+                    subs[i].done = true;
+                    side_in.push_back(*subs[i].in);
+                }
+            int device = 0;
+            RAMBL_CUDA(cudaGetDevice(&device));
+            RAMBL_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+            side_thread = std::thread([this, device] {
+                try
+                {
+                    RAMBL_CUDA(cudaSetDevice(device));
+                    InferParams p2 = prm;
+                    p2.level_synchronous = true;
+                    infer_batch(side_in, p2, side_out, side_stats, side_stream);
+                }
+                catch (...) { side_error = std::current_exception(); }
+            });
+        }
         // ---- fill the static tables (pinned) on the workers, one copy to the device
         p_static.reserve(stat_bytes);
         d_static.reserve(stat_bytes);
@@ -1257,8 +1313,38 @@ struct Engine
                 cd.node = s.g->end_node;
                 s.cands.push_back(cd);
             }
-            close_result(s, false);  // "$": sort + merge_strains; the walk is over, the strains keep their slots
-            ++taken;
+            if (!plans[take[k]].handoff)
+            {
+                close_result(s, false);  // "$": sort + merge_strains; the walk is over, the strains keep their slots
+                ++taken;
+                continue;
+            }
+            // the walk stopped in front of a level that holds "$" next to other nodes: the level-synchronous path takes the
+            // subgroup over exactly there (candidates, presence flags, free slots, the level's nodes)
+            {
+                const WalkSub& w = hs[k];
+                std::vector<WalkCand> wc(r.n_cands);
+                std::vector<unsigned char> pres((size_t)s.R);
+                std::vector<int> fs((size_t)std::max(r.free_top, 0));
+                if (r.n_cands) RAMBL_CUDA(cudaMemcpy(wc.data(), w.cand[r.cand_buf & 1], sizeof(WalkCand) * wc.size(), cudaMemcpyDeviceToHost));
+                RAMBL_CUDA(cudaMemcpy(pres.data(), w.present, pres.size(), cudaMemcpyDeviceToHost));
+                if (!fs.empty()) RAMBL_CUDA(cudaMemcpy(fs.data(), w.free_slots, sizeof(int) * fs.size(), cudaMemcpyDeviceToHost));
+                for (int c = 0; c < r.n_cands; ++c)
+                {
+                    s.cands[c].node = wc[c].node;
+                    s.cands[c].hash = wc[c].hash;
+                    s.cands[c].len = wc[c].len;
+                }
+                s.present.assign(pres.begin(), pres.end());
+                s.free_slots.assign(fs.begin(), fs.end());
+                s.cur = plans[take[k]].handoff_cur;
+                s.mark.assign(s.g->n_nodes, -1);
+                s.epoch = nl;
+                s.levels = nl - 1;
+                s.branching = r.branching != 0;
+                s.done = s.cands.empty();
+                if (s.done) close_result(s, false);
+            }
         }
         // subgroups the kernel gave up on start over on the level-synchronous path: wipe what the walk wrote
         for (size_t i : redo)
@@ -1323,7 +1409,7 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
     // the device-resident walk takes every subgroup it can; the level-synchronous loop below solves the rest
     {
         const char* ev = getenv("RAMBL_WALK");
-        const int mode = ev ? atoi(ev) : walk_mode();
+        const int mode = prm.level_synchronous ? 0 : (ev ? atoi(ev) : walk_mode());
         if (mode != 0)
         {
             const char* enb = getenv("RAMBL_WALK_NB");
@@ -1382,11 +1468,20 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
     RAMBL_CUDA(cudaStreamSynchronize(stream));
     E.collect_kernel_times();
     const double ms_times = since(w0);
+    E.join_side();
+    {
+        const EngineStats& q = E.side_stats;
+        stats.launches += q.launches; stats.level_steps += q.level_steps; stats.draws += q.draws;
+        stats.loglik_updates += q.loglik_updates; stats.gibbs_ms += q.gibbs_ms; stats.gibbs_launches += q.gibbs_launches;
+        stats.gibbs_bytes += q.gibbs_bytes; stats.h2d_bytes += q.h2d_bytes; stats.d2h_bytes += q.d2h_bytes;
+        stats.gibbs_rounds += q.gibbs_rounds; stats.gibbs_passes += q.gibbs_passes;
+    }
     // ---- gather
     for (size_t i = 0; i < E.subs.size(); ++i)
     {
         Sub& s = E.subs[i];
         SubgroupResult& r = out[i];
+        if (s.side >= 0) { r = std::move(E.side_out[s.side]); continue; }
         r.status = s.status;
         r.draws = s.draws;
         r.levels = s.levels;

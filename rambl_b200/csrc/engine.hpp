@@ -24,6 +24,7 @@ struct InferParams
     float diff = 0.01f;   // --diff-rate
     bool assign = true;   // run read_assign and the final sort
     bool keep_loglik = false;  // also return the per-read log-likelihood rows of the inferred strains
+    bool level_synchronous = false;  // this call: the level-synchronous path only (the side batch of subgroups the walk cannot take)
 };
 
 struct StrainResult
@@ -65,6 +66,7 @@ struct EngineStats
     long long gibbs_rounds = 0, gibbs_passes = 0;  // rounds of 32 speculative draws / passes needed to settle them
     float walk_ms = 0;             // CUDA-event time of the device-resident walk kernel
     int walk_launches = 0;
+    int offtable_levels = 0;       // graph levels on which a one-letter strain label can meet a multi-letter read string
     long long walk_bytes = 0;      // its algorithmic bytes: the Gibbs bytes + 16 B per log-likelihood update + 16 B per weight
 };
 

@@ -18,8 +18,8 @@
 // Mapping.  Real insertion levels are SMALL (a handful of letters against a profile of a dozen columns, tens to
 // hundreds of strings), so a warp per problem leaves most lanes idle and one oversized problem used to size the
 // shared memory of every CTA.  Problems are therefore dealt into SIZE CLASSES by their longest string; a class
-// gives each problem a group of G lanes (8, 16 or 32) of a CTA and a shared-memory region sized for
-// the class, so a CTA of the smallest class solves 16 problems at once.  Within a group:
+// gives each problem a group of G lanes (1, 8, 16 or 32) of a CTA and a shared-memory region sized for
+// the class, so a CTA of the smallest class solves 128 problems at once (one lane each).  Within a group:
 //   * profile columns have a stable id (creation order); `ord` maps profile position -> id, so a column
 //     insertion only shifts `ord`; letters live column-major in global scratch (colchar[id][row]);
 //   * the per-column sums against every letter class (what a DP cell needs) are kept INCREMENTALLY: aligning a
@@ -353,9 +353,12 @@ void upload_scores()
 }
 
 // size classes: a problem starts in the first class that holds its longest string
+// The first class is what real insertion levels look like (homopolymer indels: hundreds of strings of 1-4 letters, a
+// profile of 2-4 columns): a 3x3 DP has nothing to spread over lanes, so there a problem is ONE lane -- 128 problems per
+// CTA, sorted by their number of strings so that the lanes of a warp run the same number of steps.
 struct MsaClass { int LM, WM, G; };
-const MsaClass kClasses[] = {{8, 16, 8}, {16, 32, 8}, {32, 64, 16}, {63, 255, 32}};
-constexpr int kNumClasses = 4;  // + the global-memory class, index kNumClasses
+const MsaClass kClasses[] = {{4, 8, 1}, {8, 16, 8}, {16, 32, 8}, {32, 64, 16}, {63, 255, 32}};
+constexpr int kNumClasses = 5;  // + the global-memory class, index kNumClasses
 
 template <int G, int GROUPS>
 void launch_class(const MsaArgs& a, cudaStream_t st)
@@ -437,7 +440,11 @@ void msa_sp_align_batch(const MsaBatch& in, MsaResult& out, cudaStream_t stream)
     {
         std::vector<int>& list = todo[c];
         if (list.empty()) continue;
-        std::sort(list.begin(), list.end());
+        // longest problems first, neighbours of similar length: the lanes / groups of a warp finish together
+        std::sort(list.begin(), list.end(), [&](int x, int y) {
+            const int nx = in.prob_seq_off[x + 1] - in.prob_seq_off[x], ny = in.prob_seq_off[y + 1] - in.prob_seq_off[y];
+            return nx != ny ? nx > ny : x < y;
+        });
         const int n = (int)list.size();
         const bool global = c == kNumClasses;
         int WM, LM, G;
@@ -473,6 +480,7 @@ void msa_sp_align_batch(const MsaBatch& in, MsaResult& out, cudaStream_t stream)
         a.WM = WM; a.LM = LM; a.region = region; a.gtables = global ? d_tables.p : nullptr;
         RAMBL_CUDA(cudaEventRecord(e0, stream));
         if (global) launch_class<32, 4>(a, stream);
+        else if (G == 1) launch_class<1, 128>(a, stream);
         else if (G == 8) launch_class<8, 16>(a, stream);
         else if (G == 16) launch_class<16, 8>(a, stream);
         else launch_class<32, 2>(a, stream);  // 100 KB of tables per problem: two per SM

@@ -792,6 +792,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
         r.draws = n_draws; r.loglik_updates = n_updates; r.weight_pairs = n_pairs; r.gibbs_bytes = n_gbytes;
         r.rounds = rounds; r.passes = passes;
         r.sum_S = sum_S; r.gibbs_levels = n_glev; r.unstaged_levels = n_unstaged; r.max_S = max_S; r.pad = 0;
+        r.free_top = ws.v[V_FREE]; r.branching = ws.v[V_BRANCH]; r.cand_buf = ws.v[V_CB]; r.pad2 = 0;
         *res = r;
         if (prm.counters)
         {

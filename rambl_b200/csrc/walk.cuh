@@ -50,6 +50,7 @@ struct WalkResult
     unsigned long long rounds, passes;
     long long sum_S;                           // candidate strains summed over the Gibbs levels
     int gibbs_levels, unstaged_levels, max_S, pad;
+    int free_top, branching, cand_buf, pad2;   // walk state at the stop: free-slot stack height, the branching flag, which candidate buffer
 };
 
 struct WalkSub
