@@ -587,7 +587,8 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
         const size_t N = b->subs.size();
         bool fresh = b->threaded_upto == 0 && b->msa.problems() == 0;
         for (auto& sp : b->subs) fresh = fresh && !sp->built;
-        const size_t n_chunks = N >= 96 ? 4 : (N >= 16 ? 2 : 1);
+        // small batches gain nothing from chunks (their chains are latency-bound and get clusters instead)
+        const size_t n_chunks = N >= 192 ? 4 : (N >= 96 ? 2 : 1);
         if (!fresh || n_chunks == 1)
         {   // nothing to overlap (or a batch that is partly built already): the two calls, one after the other
             int rc = rambl_batch_build_graphs(b);
@@ -601,7 +602,7 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
         int device = 0;
         RAMBL_CUDA(cudaGetDevice(&device));
         std::atomic<size_t> next(0);
-        std::mutex mu;
+        std::mutex mu, build_mu;
         std::string what;
         int code = RAMBL_OK;
         const auto w0 = std::chrono::steady_clock::now();
@@ -619,7 +620,10 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
                         if (c >= n_chunks || code != RAMBL_OK) break;
                     }
                     const size_t lo = N * c / n_chunks, hi = N * (c + 1) / n_chunks;
-                    // ---- graphs of this chunk: splice, align the insertion levels on the device, finish
+                    // ---- graphs of this chunk: splice, align the insertion levels on the device, finish.  One chunk is
+                    // built at a time, on all host threads -- the other driver is in its device phase meanwhile; two
+                    // builds at once would only share the cores and leave the device idle until both are done.
+                    std::unique_lock<std::mutex> build_lock(build_mu);
                     std::vector<MsaBatch> local(hi - lo);
                     parallel_for(lo, hi, [&](size_t i) {
                         Subgroup& s = *b->subs[i];
@@ -647,6 +651,7 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
                         s.input.graph = &s.graph;
                         s.built = true;
                     });
+                    build_lock.unlock();
                     // ---- strain search of this chunk
                     std::vector<SubgroupInput> in;
                     for (size_t i = lo; i < hi; ++i) in.push_back(b->subs[i]->input);
