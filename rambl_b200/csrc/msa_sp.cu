@@ -458,7 +458,10 @@ void msa_sp_align_batch(const MsaBatch& in, MsaResult& out, cudaStream_t stream)
             WM = (int)wm;
             G = 32;
         }
-        const size_t region = msa_region_bytes(WM, LM);
+        size_t region = msa_region_bytes(WM, LM);
+        // one lane per problem: the lanes of a warp walk their regions in step, so the region stride must be an odd
+        // number of 4-byte words or all 32 lanes would sit on two shared-memory banks
+        if (!global && G == 1) while ((region / 4) % 2 == 0) region += 4;
         std::vector<long long> cco(n + 1, 0), ro(n + 1, 0);
         for (int k = 0; k < n; ++k)
         {
