@@ -1064,6 +1064,10 @@ struct Engine
                 }
         }
         if (take.empty()) return 0;
+        // CTAs are handed to the SMs in launch order: the subgroups with the most graph nodes (more variant nodes, more
+        // candidate strains, longer chains) go first, so that the last wave is made of the short walks
+        if (!getenv("RAMBL_WALK_NOSORT"))
+            std::stable_sort(take.begin(), take.end(), [&](int x, int y) { return subs[x].g->n_nodes > subs[y].g->n_nodes; });
         if (take.size() < n)
         {   // the rest: level-synchronous, concurrently (see side_in)
             for (size_t i = 0; i < n; ++i)
