@@ -79,16 +79,19 @@ size_t walk_smem_bytes(int nb, int tile_S, bool cluster)
 
 namespace {
 
-// CL: one CLUSTER of CTAs per subgroup.  Rank 0 walks the graph exactly as the single-CTA kernel does; the other
-// ranks wait at a cluster barrier and join for the Gibbs chains only, each adding NB blocks of 32 draws to a round
-// (gibbs_w_chain<.., CL = true>): the chain is the one part of a level that is sequential, so it is the part that
-// gets the extra SMs when a batch has fewer subgroups than the GPU has SMs.
+// CL: one CLUSTER of CTAs per subgroup, for batches with fewer subgroups than the GPU has SMs.  All CTAs of the cluster
+// walk the levels in step: the data-parallel phases of a level (slot copies, read set, log-likelihood update, weights,
+// hard_clustering) are split over the threads of the whole cluster with cluster barriers in between, every CTA adds NB
+// blocks of 32 draws to a round of the Gibbs chain (gibbs_w_chain<.., CL = true>), and rank 0 alone does the
+// bookkeeping between levels and tells the others what the next level looks like through a small descriptor in global
+// memory (w->helper: candidates, buffer, copies, branching flag, stop code).
 template <int NB, bool CL>
 __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const WalkSub* __restrict__ subs, WalkParams prm, int tile_S)
 {
     constexpr int NS = 4;
     constexpr int NT = 32 * NB;
     const int crank = CL ? (int)cluster_ctarank() : 0, csize = CL ? (int)cluster_nctarank() : 1;
+#define PHASE_BARRIER() do { if (CL) cluster_barrier(); else __syncthreads(); } while (0)
     const WalkSub* __restrict__ w = subs + (CL ? cluster_id_x() : blockIdx.x);
     extern __shared__ __align__(128) unsigned char walk_smem[];
     unsigned char* sp = walk_smem;
@@ -169,29 +172,11 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
     int n_glev = 0, n_unstaged = 0, max_S = 0;
 
     int* const helper = w->helper;
-    if (CL && crank != 0)
+    const int gtid = crank * NT + tid, GT = csize * NT;      // this thread / all threads of the subgroup's CTA(s)
+    const int gwarp = crank * NB + (tid >> 5), GW = csize * NB;
+    if (tid == 0) { mbar_init(&gs.bars[0], 1); mbar_init(&gs.bars[1], 1); }
+    if (crank == 0 && tid == 0)
     {
-        // ---- a helper CTA: nothing but the Gibbs chains of its subgroup, as block rank * NB .. of every round
-        if (tid == 0) { mbar_init(&gs.bars[0], 1); mbar_init(&gs.bars[1], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        __syncthreads();
-        for (;;)
-        {
-            cluster_barrier();  // rank 0 has published the next chain (or the end of the walk)
-            if (__ldcg(helper) == 0) break;
-            const int S = __ldcg(helper + 1), D = __ldcg(helper + 2), nsweeps = __ldcg(helper + 3);
-            double* const norms = W + (long long)S * padded_draws(D);
-            int nb = (int)min((size_t)NB, gs.wbuf_doubles / (2 * (size_t)S * 32));
-            if (nb == 0) nb = NB;
-            gibbs_w_chain<NB, NS, false, CL>(gs, uses0, uses1, nb, S, D, nsweeps, true, W, reinterpret_cast<int*>(norms + D),
-                                             prm.uniforms, ab_io, rounds, passes, prm.counters, crank, csize);
-        }
-        return;
-    }
-    if (tid == 0)
-    {
-        mbar_init(&gs.bars[0], 1);
-        mbar_init(&gs.bars[1], 1);
         // the root strain, Strain(100,e) (NonparametricClustering.cpp:281); level 0 extends it by "^" and sets abundance 1
         WalkCand c;
         c.slot = 0; c.node = 0; c.tail = 0; c.pad = 0; c.ab = 1.0;
@@ -203,6 +188,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
         for (int k = 1; k < cap; ++k) free_slots[k - 1] = cap - k;  // the stack hands out slots 1, 2, ..
         ws.v[V_NCAND] = 1; ws.v[V_CB] = 0; ws.v[V_BRANCH] = 0; ws.v[V_TRAIL] = 1; ws.v[V_FREE] = cap - 1;
         ws.v[V_NOPS] = 0; ws.v[V_STATUS] = -1; ws.v[V_D] = 0;
+        if (CL) { helper[0] = 1; helper[1] = 0; helper[2] = 0; helper[3] = 0; helper[4] = -1; }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -210,7 +196,14 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
     int level = 0;
     for (; level < n_levels; ++level)
     {
-        const int S = ws.v[V_NCAND], cb = ws.v[V_CB], n_ops = ws.v[V_NOPS];
+        int S, cb, n_ops, branch;
+        if (CL)
+        {
+            cluster_barrier();  // rank 0 has finished the bookkeeping of the previous level
+            S = __ldcg(helper); cb = __ldcg(helper + 1); n_ops = __ldcg(helper + 2); branch = __ldcg(helper + 3);
+            if (__ldcg(helper + 4) >= 0) break;
+        }
+        else { S = ws.v[V_NCAND]; cb = ws.v[V_CB]; n_ops = ws.v[V_NOPS]; branch = ws.v[V_BRANCH]; }
         const WalkCand* const cs = w->cand[cb];
         WalkCand* const nx = w->cand[cb ^ 1];
         // ---- slot copies queued by the last extension (children beyond the first take a copy of their parent)
@@ -219,24 +212,25 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
             const int2 op = ops[o];
             const double* __restrict__ src = ll + (long long)op.x * R;  // distinct slots: the rows never overlap
             double* __restrict__ dst = ll + (long long)op.y * R;
-            for (int x = tid; x < R; x += 4 * NT)
+            for (int x = gtid; x < R; x += 4 * GT)
             {
                 double v[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = (x + k * NT < R) ? src[x + k * NT] : 0.0;
+                for (int k = 0; k < 4; ++k) v[k] = (x + k * GT < R) ? src[x + k * GT] : 0.0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) if (x + k * NT < R) dst[x + k * NT] = v[k];
+                for (int k = 0; k < 4; ++k) if (x + k * GT < R) dst[x + k * GT] = v[k];
             }
-            for (int q = tid; q < 36; q += NT) sub[(long long)op.y * 36 + q] = sub[(long long)op.x * 36 + q];
+            if (crank == 0)
+                for (int q = tid; q < 36; q += NT) sub[(long long)op.y * 36 + q] = sub[(long long)op.x * 36 + q];
         }
         if (level == n_levels - 1) break;  // "$": the host closes the result (sort + merge_strains)
         if (S == 0) break;
         const int e0 = lvl_ent_off[level], m = lvl_ent_off[level + 1] - e0;
         const int mo = lvl_moff[level];  // -1: every entry of the level is one letter; else its entries' (offset, length) table
-        const int mode = (m > 0) ? (ws.v[V_BRANCH] ? MODE_GIBBS : MODE_HARD) : MODE_NONE;
+        const int mode = (m > 0) ? (branch ? MODE_GIBBS : MODE_HARD) : MODE_NONE;
         if (S > WALK_SMAX)
         {
-            if (tid == 0) ws.v[V_STATUS] = WALK_TOO_MANY_STRAINS;
+            if (crank == 0 && tid == 0) ws.v[V_STATUS] = WALK_TOO_MANY_STRAINS;
             break;
         }
         for (int s = tid; s < S; s += NT)
@@ -247,7 +241,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
             ws.lab_off[s] = label_off[c.node];
             ws.lab_len[s] = label_off[c.node + 1] - label_off[c.node];
         }
-        __syncthreads();
+        PHASE_BARRIER();  // the slot copies are complete (all CTAs), the candidates are in shared memory
         int D = 0, nsweeps = 0;
         if (mode != MODE_NONE)
         {
@@ -277,7 +271,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
             __syncthreads();
             D = ws.v[V_D];
             // "new" = first time any strain sees the read; hard_clustering only looks at the flag on collapsed nodes
-            for (int r = tid; r < m; r += NT)
+            for (int r = gtid; r < m; r += GT)
             {
                 const unsigned er = ent_rid[e0 + r];
                 const int rid = (int)(er & 0x7fffffffu);
@@ -291,10 +285,10 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                     draw_mate[d0 + k] = pair_val[po + cn - k - 1];
                 }
             }
-            __syncthreads();
+            PHASE_BARRIER();
             if (mode == MODE_GIBBS)
             {   // a mate no strain has seen yet does not count
-                for (int d = tid; d < D; d += NT)
+                for (int d = gtid; d < D; d += GT)
                 {
                     const int mate = draw_mate[d];
                     if (mate >= 0 && !present[mate]) draw_mate[d] = -1;
@@ -302,8 +296,8 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
             }
             else
             {   // Strain::logprob(uid) creates the mate's entry
-                __syncthreads();
-                for (int d = tid; d < D; d += NT)
+                PHASE_BARRIER();
+                for (int d = gtid; d < D; d += GT)
                 {
                     const int mate = draw_mate[d];
                     if (mate >= 0) present[mate] = 1;
@@ -312,7 +306,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
             nsweeps = (mode == MODE_GIBBS) ? min(prm.n, 40000 / max(D, 1)) : 0;
             // ---- log-likelihood update: ll[strain][read] += log p(read letters | strain letters)
             // the strains' log tables first (Strain::logprob(a,b) = log(sub[a,b]) - log(comp[a]), Strain.cpp:130-133) ...
-            for (int q = tid; q < S * 36; q += NT)
+            for (int q = gtid; q < S * 36; q += GT)
             {
                 const int st = q / 36, k = q - st * 36;
                 const double* sb = sub + (long long)ws.slot[st] * 36;
@@ -321,7 +315,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                 lut_g[q] = log(sb[k]) - log(c);
             }
             for (int st = tid; st < S; st += NT) ws.la[st] = (ws.lab_len[st] == 1) ? letter_code(label_chars[ws.lab_off[st]]) : 8;
-            __syncthreads();
+            PHASE_BARRIER();
             // ... then one thread per read-pool entry, four strains in flight (independent rows): a read has one entry per
             // level, except the entries flagged as repeats, which are added afterwards in entry order
             auto entry_term = [&](int st, int r, const char* rs, int rl) -> double {
@@ -347,7 +341,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                 }
                 return d;
             };
-            for (int r = tid; r < m; r += NT)
+            for (int r = gtid; r < m; r += GT)
             {
                 const unsigned er = ent_rid[e0 + r];
                 if (er >> 31) continue;
@@ -374,8 +368,8 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
             }
             if (lvl_dup[level])
             {
-                __syncthreads();
-                for (int st = tid; st < S; st += NT)
+                PHASE_BARRIER();
+                for (int st = gtid; st < S; st += GT)
                 {
                     double* row = ll + (long long)ws.slot[st] * R;
                     for (int r = 0; r < m; ++r)
@@ -387,12 +381,12 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                     }
                 }
             }
-            __syncthreads();
+            PHASE_BARRIER();
             // ---- weights: exp(loglik(read) + loglik(mate)) per (draw, strain), tile-major (dpm_dev.cuh)
             double* const wt = W;
             double* const norms = W + (long long)S * padded_draws(D);
             int* const codes = reinterpret_cast<int*>(norms + D);
-            for (int d = tid; d < D; d += NT)
+            for (int d = gtid; d < D; d += GT)
             {
                 const int r = draw_entry[d];
                 const int rid = (int)(ent_rid[e0 + r] & 0x7fffffffu);
@@ -421,18 +415,18 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
             // the Gibbs chain reads its tiles through the async proxy (bulk copies): order the generic-proxy stores
             asm volatile("fence.proxy.async;" ::: "memory");
             __threadfence_block();
-            __syncthreads();
+            PHASE_BARRIER();
             if (mode == MODE_HARD)
             {
                 // ---- hard_clustering: soft assignment, masses and substitution counts (deterministic: no atomics)
-                for (int d = tid; d < D; d += NT)
+                for (int d = gtid; d < D; d += GT)
                 {
                     double t = 0;
                     for (int s = 0; s < S; ++s) t += ws.ab[s] * wt[weight_index(d, s, S)];
                     norms[d] = t;
                 }
-                __syncthreads();
-                for (int s = warp; s < S; s += NB)
+                PHASE_BARRIER();
+                for (int s = gwarp; s < S; s += GW)
                 {
                     double acc[37];
 #pragma unroll
@@ -480,27 +474,22 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
                         if (lane == 0)
                         {
-                            if (k == 0) ws.al[s] = v;
+                            if (k == 0) ab_io[s] = v;
                             else if (v != 0) sb[k - 1] += v;
                         }
                     }
                 }
+                PHASE_BARRIER();  // the increments of every strain, whichever CTA's warp summed them
+                for (int s = tid; s < S; s += NT) ws.al[s] = CL ? __ldcg(ab_io + s) : ab_io[s];
             }
             else
             {
                 // ---- np_bayes_clustering: the sequential Gibbs chain, NB blocks of 32 draws per round
-                for (int s = tid; s < S; s += NT) ab_io[s] = ws.ab[s];
-                __syncthreads();
                 // as many 32-draw blocks per round as the level's tiles leave room for in the tile buffers; a level too wide
                 // for even one block reads its weights from L1/L2 with all NB blocks
                 int nb = (int)min((size_t)NB, gs.wbuf_doubles / (2 * (size_t)S * 32));
                 if (nb == 0) nb = NB;
-                if (CL)
-                {   // the helper CTAs of the cluster join for the chain
-                    if (tid == 0) { helper[1] = S; helper[2] = D; helper[3] = nsweeps; helper[0] = 1; }
-                    cluster_barrier();
-                }
-                gibbs_w_chain<NB, NS, false, CL>(gs, uses0, uses1, nb, S, D, nsweeps, true, wt, codes, prm.uniforms, ab_io, rounds, passes,
+                gibbs_w_chain<NB, NS, false, CL>(gs, uses0, uses1, nb, S, D, nsweeps, true, wt, codes, prm.uniforms, ws.ab, rounds, passes,
                                                  prm.counters, crank, csize);
                 if (warp == 0)
                 {   // normalise the masses; fold the averaged letter counts into the models (lines 217-243)
@@ -510,7 +499,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                     for (int s = lane; s < S; s += 32)
                     {
                         ws.al[s] = mass[s] / z * (double)D;
-                        if (ws.lab_len[s] == 1)
+                        if (crank == 0 && ws.lab_len[s] == 1)
                         {
                             const int la = letter_code(label_chars[ws.lab_off[s]]);
                             if (la < 6)
@@ -523,7 +512,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                     }
                 }
             }
-            if (tid == 0)
+            if (crank == 0 && tid == 0)
             {
                 n_updates += (long long)m * S;
                 n_pairs += (long long)D * S;
@@ -541,7 +530,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
         }
 
         // ---- between levels (warp 0): abundances, pruning, path extension, the 80-candidate cut, slots
-        if (warp == 0)
+        if (crank == 0 && warp == 0)
         {
             int n_keep = 0;
             int free_top = ws.v[V_FREE];
@@ -756,11 +745,16 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                 ws.v[V_BRANCH] = branching ? 1 : 0;
                 ws.v[V_TRAIL] = trail_n;
                 if (fail >= 0) ws.v[V_STATUS] = fail;
+                if (CL)
+                {   // what the other CTAs of the cluster need to know about the next level
+                    helper[0] = K; helper[1] = cb ^ 1; helper[2] = ws.v[V_NOPS]; helper[3] = branching ? 1 : 0; helper[4] = ws.v[V_STATUS];
+                }
             }
         }
         __syncthreads();
-        if (ws.v[V_STATUS] >= 0) break;
+        if (!CL && ws.v[V_STATUS] >= 0) break;
     }
+    if (CL && crank != 0) return;  // rank 0 writes the result
     __syncthreads();
     // ---- result: the candidates at "$" with their paths, or why the walk stopped
     const int status = ws.v[V_STATUS] >= 0 ? ws.v[V_STATUS] : (level == n_levels - 1 && ws.v[V_NCAND] > 0 ? WALK_DONE : WALK_NO_CANDS);
@@ -799,9 +793,8 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
             atomicAdd(&prm.counters[0], rounds);
             atomicAdd(&prm.counters[1], passes);
         }
-        if (CL) helper[0] = 0;  // the walk is over: release the helper CTAs
     }
-    if (CL) cluster_barrier();
+#undef PHASE_BARRIER
 }
 
 template <int NB, bool CL>
