@@ -1224,10 +1224,11 @@ struct Engine
         int cluster = 1;
         if (nb == 8)
         {
-            // (measured on configs[1]: 8 CTAs 1.65x, 4 CTAs 1.3x, 2 CTAs 0.95x the single CTA -- the per-pass exchange
-            // and cluster barrier eat what two CTAs gain)
+            // (measured on configs[1]: 8 CTAs 2.2x, 4 CTAs 1.6x, 2 CTAs 1.05x the single CTA -- the per-pass exchange and
+            // the cluster barriers eat most of what two CTAs gain)
             if (take.size() <= 16) cluster = 8;
             else if (take.size() <= 32) cluster = 4;
+            else if (take.size() <= 72) cluster = 2;
             if (forced_cluster > 0) cluster = forced_cluster;
         }
         while (tile + 4 <= WALK_SMAX && walk_smem_bytes(nb, tile + 4, cluster > 1) <= sm_bytes) tile += 4;
