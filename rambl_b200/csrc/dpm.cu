@@ -66,7 +66,12 @@ __global__ void __launch_bounds__(128) k_loglik(const StepGroup* __restrict__ gr
                 while (ii < lab_l && jj < rl) d += pair_loglik(lut, letter_code(lab[ii++]), letter_code(rs[jj++]));
             }
         }
-        atomicAdd(&row[rid], d);  // Strain::update_read_loglik; rows start at 0, so "create" == "add"
+        // Strain::update_read_loglik; rows start at 0, so "create" == "add".  A (strain, read) pair normally occurs once
+        // per level, which makes this a plain add.  A read with TWO entries on one level (graphs that are not strictly
+        // levelled) is added twice in whatever order the atomics land: (ll + d1) + d2 and (ll + d2) + d1 can differ in the
+        // last bit.  The device walk (walk.cu) adds such repeats in entry order, like the reference; this kernel only serves
+        // subgroups the walk hands over.
+        atomicAdd(&row[rid], d);
     }
 }
 
@@ -656,7 +661,10 @@ template <int NG>
 static void launch_gibbs(const StepLaunch& L, int smem_S, cudaStream_t st)
 {
     const size_t smem = gibbs_smem_bytes(NG, smem_S);
-    static size_t configured = 0;
+    static size_t configured_on[64] = {0};  // per device: the attribute belongs to the device's copy of the kernel
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& configured = configured_on[dev & 63];
     if (smem > configured)
     {
         RAMBL_CUDA(cudaFuncSetAttribute(k_gibbs<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -676,7 +684,10 @@ template <int NB, int NS>
 static void launch_gibbs_w_ns(const StepLaunch& L, int smem_S, cudaStream_t st)
 {
     const size_t smem = gibbs_w_smem_bytes(NB, smem_S);
-    static size_t configured = 0;
+    static size_t configured_on[64] = {0};  // per device: the attribute belongs to the device's copy of the kernel
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& configured = configured_on[dev & 63];
     if (smem > configured)
     {
         RAMBL_CUDA(cudaFuncSetAttribute(k_gibbs_w<NB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

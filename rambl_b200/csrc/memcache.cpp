@@ -20,6 +20,14 @@ Cache& cache()
     static Cache* c = new Cache;  // never destroyed: blocks may be released after main() returns
     return *c;
 }
+int current_device()
+{
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; }
+    return d;
+}
+// device blocks are listed per device: granted sizes are powers of two below 2^48, the device goes above
+size_t device_key(size_t granted, int device) { return granted | ((size_t)(device & 0xff) << 48); }
 size_t round_up(size_t bytes)
 {
     size_t g = 256;
@@ -34,7 +42,7 @@ void* cached_device_alloc(size_t bytes, size_t* granted)
     *granted = g;
     {
         std::lock_guard<std::mutex> lk(cache().mu);
-        auto it = cache().device.find(g);
+        auto it = cache().device.find(device_key(g, current_device()));
         if (it != cache().device.end())
         {
             void* p = it->second;
@@ -56,8 +64,13 @@ void* cached_device_alloc(size_t bytes, size_t* granted)
 void cached_device_free(void* p, size_t granted)
 {
     if (!p) return;
+    // a block goes back to the list of the device it lives on (one process may drive several devices)
+    int dev = current_device();
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice) dev = at.device;
+    else cudaGetLastError();
     std::lock_guard<std::mutex> lk(cache().mu);
-    cache().device.insert({granted, p});
+    cache().device.insert({device_key(granted, dev), p});
 }
 
 void* cached_pinned_alloc(size_t bytes, size_t* granted)

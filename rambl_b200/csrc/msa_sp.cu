@@ -342,9 +342,12 @@ __global__ void __launch_bounds__(G * GROUPS) msa_sp_kernel(MsaArgs a)
     }
 }
 
-bool g_score_ready = false;
 void upload_scores()
 {
+    static bool ready_on[64] = {false};  // per device: __constant__ memory is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& g_score_ready = ready_on[dev & 63];
     if (g_score_ready) return;
     int S[NCLS][NCLS];
     for (int x = 0; x < NCLS; ++x) for (int y = 0; y < NCLS; ++y) S[x][y] = host_score(x, y);
@@ -364,7 +367,10 @@ template <int G, int GROUPS>
 void launch_class(const MsaArgs& a, cudaStream_t st)
 {
     const size_t smem = a.gtables ? 16 : a.region * (size_t)GROUPS;
-    static size_t configured = 0;
+    static size_t configured_on[64] = {0};  // per device: the attribute belongs to the device's copy of the kernel
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& configured = configured_on[dev & 63];
     if (smem > configured)
     {
         RAMBL_CUDA(cudaFuncSetAttribute(msa_sp_kernel<G, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

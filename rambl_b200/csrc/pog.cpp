@@ -30,10 +30,55 @@ namespace rambl {
 
 namespace {
 
+// The letters of a read-pool entry: one letter nearly always (a few after path collapse), so they live inline -- a
+// std::string per entry (32 bytes, 650 000 entries per 5 000-read subgroup) was the larger half of the builder's memory
+// traffic.  Longer strings (long collapsed paths) go to the heap.
+class PoolStr
+{
+public:
+    PoolStr() : n_(0) { u_.inl[0] = 0; }
+    explicit PoolStr(char c) : n_(1) { u_.inl[0] = c; }
+    PoolStr(const char* p) : n_(0) { assign(p, (uint32_t)strlen(p)); }
+    PoolStr(const PoolStr& o) : n_(0) { assign(o.data(), o.n_); }
+    PoolStr(PoolStr&& o) noexcept : n_(o.n_), u_(o.u_) { o.n_ = 0; }
+    PoolStr& operator=(const PoolStr& o) { if (this != &o) { release(); assign(o.data(), o.n_); } return *this; }
+    PoolStr& operator=(PoolStr&& o) noexcept { if (this != &o) { release(); n_ = o.n_; u_ = o.u_; o.n_ = 0; } return *this; }
+    ~PoolStr() { release(); }
+    size_t size() const { return n_; }
+    const char* data() const { return n_ <= kInline ? u_.inl : u_.heap; }
+    char operator[](size_t i) const { return data()[i]; }
+    int compare(const PoolStr& o) const
+    {
+        const int c = memcmp(data(), o.data(), std::min(n_, o.n_));
+        return c != 0 ? c : (n_ < o.n_ ? -1 : (n_ > o.n_ ? 1 : 0));
+    }
+    friend PoolStr operator+(const PoolStr& a, const PoolStr& b)
+    {
+        PoolStr r;
+        r.n_ = a.n_ + b.n_;
+        char* d = r.n_ <= kInline ? r.u_.inl : (r.u_.heap = (char*)malloc(r.n_));
+        memcpy(d, a.data(), a.n_);
+        memcpy(d + a.n_, b.data(), b.n_);
+        return r;
+    }
+
+private:
+    static constexpr uint32_t kInline = 8;
+    void assign(const char* p, uint32_t n)
+    {
+        n_ = n;
+        char* d = n <= kInline ? u_.inl : (u_.heap = (char*)malloc(n));
+        memcpy(d, p, n);
+    }
+    void release() { if (n_ > kInline) free(u_.heap); n_ = 0; }
+    uint32_t n_;
+    union { char inl[8]; char* heap; } u_;
+};
+
 struct PoolItem
 {
     int rid;
-    std::string s;
+    PoolStr s;
     int cn;
     bool operator<(const PoolItem& o) const
     {
@@ -237,7 +282,7 @@ struct GraphBuilder::Impl
                             V[v].sib.push_back(hit);
                         }
                         else if (!has_edge(u, hit)) connect(u, hit);
-                        V[hit].pool.push_back({rid, std::string(1, r[j]), rd.cn});
+                        V[hit].pool.push_back({rid, PoolStr(r[j]), rd.cn});
                         u = hit;
                         step_v();
                     }
@@ -249,7 +294,7 @@ struct GraphBuilder::Impl
                     for (int q = 0; q < len; ++q, ++j)
                     {
                         int w = add(ST_INS, r[j]);
-                        V[w].pool.push_back({rid, std::string(1, r[j]), rd.cn});
+                        V[w].pool.push_back({rid, PoolStr(r[j]), rd.cn});
                         chain.push_back(w);
                     }
                     if (chain.empty()) continue;
@@ -390,7 +435,7 @@ struct GraphBuilder::Impl
                 for (char c : aligned)
                 {
                     int w = add(ST_INS, c);
-                    V[w].pool.push_back({rid, std::string(1, c), rcn});
+                    V[w].pool.push_back({rid, PoolStr(c), rcn});
                     chain.push_back(w);
                 }
                 hang(lp.spans[t].from, lp.spans[t].to, chain);

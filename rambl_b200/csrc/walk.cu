@@ -801,7 +801,10 @@ template <int NB, bool CL>
 void launch_walk_nb(const WalkSub* d_subs, int n_subs, const WalkParams& prm, int tile_S, int cluster, cudaStream_t st)
 {
     const size_t smem = walk_smem_bytes(NB, tile_S, CL);
-    static size_t configured = 0;
+    static size_t configured_on[64] = {0};  // per device: the attribute belongs to the device's copy of the kernel
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& configured = configured_on[dev & 63];
     if (smem > configured)
     {
         RAMBL_CUDA(cudaFuncSetAttribute(k_walk<NB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -201,3 +201,57 @@ def test_config3_reads_through_the_cli_glue_equal_the_golden_input(tmp_path):
     assert sum(w["cn"]) < 0.1 * len(raw)  # the depth cap was active
     assert (w["gene"], w["pos"], w["cigar"], w["seq"], w["cn"]) == (inp["gene"], inp["pos"], inp["cigar"], inp["seq"], inp["cn"])
     assert [m for ms in w["mates"] for m in ms] == inp["pair_val"]
+
+
+def _two_gene_fixture(tmp_path):
+    fa = os.path.join(str(tmp_path), "genes.fa")
+    sam = os.path.join(str(tmp_path), "reads.sam")
+    rois = []
+    with open(fa, "w") as f, open(fa + ".fai", "w") as fi, open(sam, "w") as fs:
+        off = 0
+        for k, (seed, win) in enumerate([(41, (100, 300)), (42, (700, 880))]):
+            gene, raw, _ = synth.simulate_raw_reads(220, 60, 2 + k, seed=seed, window=win, sub_err=0.003, divergence=(0.03, 0.06))
+            name = "gene%d" % k
+            rois.append("%s:1-%d" % (name, len(gene)))
+            f.write(">%s\n" % name)
+            off += len(name) + 2
+            fi.write("%s\t%d\t%d\t60\t61\n" % (name, len(gene), off))
+            for i in range(0, len(gene), 60):
+                f.write(gene[i:i + 60] + "\n")
+            off += len(gene) + (len(gene) + 59) // 60
+            for (nm, p, cg, sq) in sorted(raw, key=lambda r: r[1]):
+                fs.write("%s_%d\t0\t%s\t%d\t30\t%s\t*\t0\t0\t%s\t%s\n" % (nm, k, name, p + 1, cg, sq, "I" * len(sq)))
+    return fa, sam, rois
+
+
+@pytest.mark.gpu
+def test_cli_several_regions_in_one_call(tmp_path):
+    """`-r` may repeat and `--roi-file` lists regions: every window of every region goes into ONE batch, and stdout is
+    what the single-region runs (the way scripts/rambl.py calls StrainCall, rambl.py:179-190) print one after the other."""
+    fa, sam, rois = _two_gene_fixture(tmp_path)
+    common = ["-q", "0", "-l", "20", "-w", "5000", fa, sam]
+    singles = ""
+    for r in rois:
+        code, out, err = run_cli(CLI, ["-r", r] + common, str(tmp_path))
+        assert code == 0, err
+        singles += out
+    code, out, err = run_cli(CLI, ["-r", rois[0], "-r", rois[1]] + common, str(tmp_path))
+    assert code == 0, err
+    assert out == singles and out.count(">contiggene0") >= 1 and out.count(">contiggene1") >= 1
+    roi_file = os.path.join(str(tmp_path), "rois.txt")
+    with open(roi_file, "w") as f:
+        f.write("# seed genes of the sample\n" + "\n".join(rois) + "\n")
+    code, out2, err = run_cli(CLI, ["--roi-file", roi_file, "--device", "0"] + common, str(tmp_path))
+    assert code == 0, err
+    assert out2 == singles
+
+
+def test_cli_several_regions_dump_inputs(tmp_path):
+    """CPU: the same, up to where the device takes over (--dump-inputs): the windows of all regions, in order."""
+    fa, sam, rois = _two_gene_fixture(tmp_path)
+    dump = os.path.join(str(tmp_path), "dump.txt")
+    code, _, err = run_cli(CLI, ["-r", rois[0], "-r", rois[1], "-q", "0", "-l", "20", "-w", "5000", fa, sam, "--dump-inputs", dump],
+                           str(tmp_path))
+    assert code == 0, err
+    wins = parse_dump(dump)
+    assert [w["name"] for w in wins] == ["gene0", "gene1"] and all(len(w["pos"]) > 50 for w in wins)
