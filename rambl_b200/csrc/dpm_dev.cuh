@@ -190,7 +190,7 @@ template <int NB, int NS, bool STAGED_ONLY, bool CL = false>
 __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& uses0, unsigned& uses1, int nb, int S, int D, int nsweeps,
                                               bool count_letters, const double* wt, const int* code, const double* U,
                                               const double* ab_in, unsigned long long& rounds, unsigned long long& passes,
-                                              unsigned long long* counters, int crank = 0, int csize = 1)
+                                              unsigned long long* counters, int crank = 0, int csize = 1, bool single = false)
 {
     constexpr int GIBBS_LIST = gibbs_list_len<NS>();
     if (!CL) { crank = 0; csize = 1; }
@@ -206,7 +206,9 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
     int* const cnt = gs.cnt;
     const int smem_S = gs.row_S;
     const size_t buf_doubles = (size_t)nb * S * 32;  // one round's tiles: the second buffer starts right behind
-    const bool staged = STAGED_ONLY || 2 * buf_doubles <= gs.wbuf_doubles;
+    // `single`: one tile buffer instead of two -- a level of many strains then still runs many blocks per round; the tiles
+    // of the next round are fetched when the round is over (the copy is exposed, but the round is twice as wide)
+    const bool staged = STAGED_ONLY || (single ? 1 : 2) * buf_doubles <= gs.wbuf_doubles;
     const int tid = threadIdx.x, lane = tid & 31, b = tid >> 5;
     const unsigned full = 0xffffffffu;
     const int Dp = padded_draws(D);
@@ -231,7 +233,7 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
     auto stage = [&](int r) {
         if (staged && tid == 0)
         {
-            const int bf = r & 1;
+            const int bf = single ? 0 : (r & 1);
             const int first = r * gnb + gb0;
             int left = min(nb, total_tiles - first);
             int stage_pos = first % tiles;
@@ -282,7 +284,7 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
         const int cd = cd_next;
         if (r + 1 < n_rounds)
         {
-            if (r + 1 < my_rounds) stage(r + 1);  // overlaps this round's arithmetic
+            if (!single && r + 1 < my_rounds) stage(r + 1);  // overlaps this round's arithmetic
             t_next += gnb;
             while (t_next >= tiles) { t_next -= tiles; ++sw_next; }
             const int dn = t_next * 32 + lane;
@@ -290,10 +292,14 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
             u_next = vn ? U[(long long)sw_next * D + dn] : 0.0;
             cd_next = (vn && count_letters) ? code[dn] : 0;
         }
-        if (staged && r < my_rounds) mbar_wait(&bars[r & 1], (((r & 1) ? uses1 : uses0) + (unsigned)(r >> 1)) & 1u);
+        if (staged && r < my_rounds)
+        {
+            if (single) mbar_wait(&bars[0], (uses0 + (unsigned)r) & 1u);
+            else mbar_wait(&bars[r & 1], (((r & 1) ? uses1 : uses0) + (unsigned)(r >> 1)) & 1u);
+        }
         unsigned long long* hpack = hpacks + (r & 1) * smem_S;
         unsigned char* hbytes = reinterpret_cast<unsigned char*>(hpack);
-        const double* wl = staged ? wbuf + (size_t)(r & 1) * buf_doubles + (size_t)b * S * 32 + lane
+        const double* wl = staged ? wbuf + (size_t)(single ? 0 : (r & 1)) * buf_doubles + (size_t)b * S * 32 + lane
                                   : wt + (long long)t_cur * S * 32 + lane;
         double off[GIBBS_NW + 1];
         off[0] = 0;
@@ -438,6 +444,8 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
 #pragma unroll
                     for (int h = 0; h < NS; ++h)
                     {
+                        hs[h] = 0; mm[h] = 0;
+                        if (32 * h >= S) continue;  // (warp-uniform) no strain up there on this level
                         const bool in = lane + 32 * h < S;
                         const unsigned long long hp = in ? hpack[lane + 32 * h] : 0ull;
                         mm[h] = in ? pm[lane + 32 * h] : 0u;
@@ -448,6 +456,7 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
 #pragma unroll
                     for (int h = 0; h < NS; ++h)
                     {
+                        if (32 * h >= S) continue;
                         const unsigned bal = __ballot_sync(full, (hs[h] | mm[h]) != 0);
                         if (hs[h] | mm[h]) list[n_list + __popc(bal & lt)] = make_uint2((unsigned)(lane + 32 * h) | (hs[h] << 8), mm[h]);
                         n_list += __popc(bal);
@@ -564,6 +573,7 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
             }
         }
         ++rounds;
+        if (single && r + 1 < my_rounds) stage(r + 1);  // every warp is past its last look at this round's tiles
         // ---- commit: letter statistics, then the masses of the next round from the exact pick counts
         // Every warp updates its own copy of the masses from the round's counts, so the next round starts without a
         // barrier.  The counts of round r stay readable until every warp has passed the first barrier of round
@@ -603,8 +613,12 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
     }
     if (staged)
     {
-        uses0 += (unsigned)((my_rounds + 1) >> 1);
-        uses1 += (unsigned)(my_rounds >> 1);
+        if (single) uses0 += (unsigned)my_rounds;
+        else
+        {
+            uses0 += (unsigned)((my_rounds + 1) >> 1);
+            uses1 += (unsigned)(my_rounds >> 1);
+        }
     }
 }
 

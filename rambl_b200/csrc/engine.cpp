@@ -1235,6 +1235,7 @@ struct Engine
         if (forced_tile > 0) tile = forced_tile;
         WalkParams wp;
         wp.n = prm.n;
+        wp.single_buffer = getenv("RAMBL_WALK_DOUBLE") ? 0 : 1;
         wp.tau = tau;
         wp.uniforms = d_U.p;
         wp.counters = d_counters.p;

@@ -487,10 +487,14 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                 // ---- np_bayes_clustering: the sequential Gibbs chain, NB blocks of 32 draws per round
                 // as many 32-draw blocks per round as the level's tiles leave room for in the tile buffers; a level too wide
                 // for even one block reads its weights from L1/L2 with all NB blocks
-                int nb = (int)min((size_t)NB, gs.wbuf_doubles / (2 * (size_t)S * 32));
+                const int nb_two = (int)min((size_t)NB, gs.wbuf_doubles / (2 * (size_t)S * 32));
+                const int nb_one = (int)min((size_t)NB, gs.wbuf_doubles / ((size_t)S * 32));
+                // a wide level: one tile buffer instead of two when that buys at least half as many blocks again
+                const bool single = prm.single_buffer && nb_two < NB && 2 * nb_one >= 3 * max(nb_two, 1);
+                int nb = single ? nb_one : nb_two;
                 if (nb == 0) nb = NB;
                 gibbs_w_chain<NB, NS, false, CL>(gs, uses0, uses1, nb, S, D, nsweeps, true, wt, codes, prm.uniforms, ws.ab, rounds, passes,
-                                                 prm.counters, crank, csize);
+                                                 prm.counters, crank, csize, single);
                 if (warp == 0)
                 {   // normalise the masses; fold the averaged letter counts into the models (lines 217-243)
                     const double* mass = gs.masses;
@@ -523,7 +527,7 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                     n_glev += 1;
                     sum_S += S;
                     max_S = max(max_S, S);
-                    if (2 * (size_t)S * 32 > gs.wbuf_doubles) n_unstaged += 1;
+                    if ((size_t)S * 32 > gs.wbuf_doubles) n_unstaged += 1;
                 }
             }
             __syncthreads();

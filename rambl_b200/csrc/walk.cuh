@@ -105,6 +105,7 @@ struct WalkSub
 struct WalkParams
 {
     int n;          // sweep cap (5000)
+    int single_buffer;  // 1: wide levels may run with one tile buffer (more blocks per round, the tile copy exposed)
     double tau;
     const double* uniforms;               // the std::mt19937(1234) canonical stream
     unsigned long long* counters;         // [0] rounds, [1] passes, [2] rounds that did not settle
