@@ -924,7 +924,7 @@ struct Engine
         if (g.n_nodes < 2 || g.end_node < 0) { p.reason = 8; return; }
         std::vector<int> mark(g.n_nodes, -1);
         std::vector<int> cur(1, 0), nxt;
-        std::vector<int> seen_rid(std::max(1, g.n_reads), -1);
+        std::vector<int> seen_rid(std::max(1, g.n_reads), -1), mult(std::max(1, g.n_reads), 0);
         p.lvl_ent_off.assign(1, 0);
         int level = 0;
         bool ok = true, ended = false;
@@ -954,8 +954,9 @@ struct Engine
                     {
                         const int rid = g.pool_rid[e], cn = g.pool_cn[e], len = g.pool_str_off[e + 1] - g.pool_str_off[e];
                         if (cn < 1 || cn > 255 || len < 1 || len > 255) { ok = false; p.reason = 4; break; }
-                        if (seen_rid[rid] == level) dup = 1;  // its further entries are added after the first, in entry order
-                        seen_rid[rid] = level;
+                        // further entries of a read on one level are added after the first, in entry order
+                        if (seen_rid[rid] == level) { mult[rid] += 1; dup = (unsigned char)std::min(255, std::max<int>(dup, mult[rid])); }
+                        else { seen_rid[rid] = level; mult[rid] = 0; }
                         if (len > 1) multi = true;
                         m += 1; D += cn; chars += len;
                     }

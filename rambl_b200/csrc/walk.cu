@@ -341,32 +341,39 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                 }
                 return d;
             };
-            for (int r = gtid; r < m; r += GT)
+            // (pass 0: the first entry of every read; pass 1: second entries -- distinct reads again, so still one thread per
+            // entry -- after a barrier; a read with three or more entries on a level takes the ordered loop below)
+            const int dup_depth = lvl_dup[level];
+            for (int pass = 0; pass < (dup_depth == 1 ? 2 : 1); ++pass)
             {
-                const unsigned er = ent_rid[e0 + r];
-                if (er >> 31) continue;
-                const int rid = (int)er;
-                const char* rs = mo >= 0 ? m_chars + m_soff[mo + r] : ent_char1 + e0 + r;
-                const int rl = mo >= 0 ? (int)m_len[mo + r] : 1;
-                for (int s0 = 0; s0 < S; s0 += 4)
+                if (pass) PHASE_BARRIER();
+                for (int r = gtid; r < m; r += GT)
                 {
-                    double dv[4], old[4];
-                    double* pr[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    const unsigned er = ent_rid[e0 + r];
+                    if ((int)(er >> 31) != pass) continue;
+                    const int rid = (int)(er & 0x7fffffffu);
+                    const char* rs = mo >= 0 ? m_chars + m_soff[mo + r] : ent_char1 + e0 + r;
+                    const int rl = mo >= 0 ? (int)m_len[mo + r] : 1;
+                    for (int s0 = 0; s0 < S; s0 += 4)
                     {
-                        const int st = min(s0 + k, S - 1);
-                        dv[k] = entry_term(st, r, rs, rl);
-                        pr[k] = ll + (long long)ws.slot[st] * R + rid;
+                        double dv[4], old[4];
+                        double* pr[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                        {
+                            const int st = min(s0 + k, S - 1);
+                            dv[k] = entry_term(st, r, rs, rl);
+                            pr[k] = ll + (long long)ws.slot[st] * R + rid;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) old[k] = *pr[k];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (s0 + k < S) *pr[k] = old[k] + dv[k];
                     }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) old[k] = *pr[k];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (s0 + k < S) *pr[k] = old[k] + dv[k];
                 }
             }
-            if (lvl_dup[level])
+            if (dup_depth > 1)
             {
                 PHASE_BARRIER();
                 for (int st = gtid; st < S; st += GT)

@@ -64,7 +64,7 @@ struct WalkSub
     int end_node;
     int n_levels;                   // levels of the walk; the last one holds "$" alone
     const int* lvl_ent_off;         // [n_levels+1] read-pool entries of a level, in the order the level's nodes list them
-    const unsigned char* lvl_dup;   // [n_levels] some read has more than one entry on the level
+    const unsigned char* lvl_dup;   // [n_levels] the most FURTHER entries any read has on the level (0: every read once)
     const unsigned* ent_rid;        // [entries] unique read id; bit 31: a further entry of a read already listed on this level
     const unsigned char* ent_cn;    // [entries] copies
     const char* ent_char1;          // [entries] the entry's letter (levels whose entries are all one letter: nearly all)
