@@ -190,8 +190,13 @@ template <int NB, int NS, bool STAGED_ONLY, bool CL = false>
 __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& uses0, unsigned& uses1, int nb, int S, int D, int nsweeps,
                                               bool count_letters, const double* wt, const int* code, const double* U,
                                               const double* ab_in, unsigned long long& rounds, unsigned long long& passes,
-                                              unsigned long long* counters, int crank = 0, int csize = 1, bool single = false)
+                                              unsigned long long* counters, int crank = 0, int csize = 1, int tile_mode = 0)
 {
+    // tile_mode 0: two tile buffers, the next round's tiles arrive while this round settles; 1: one buffer -- a level of
+    // many strains then still runs many blocks per round, the tiles of the next round are fetched when the round is over
+    // (the copy is exposed, but the round is wider); 2: the weights of the WHOLE level fit the buffers -- one copy when
+    // the chain starts, nothing per round (every sweep re-reads the same tiles from shared memory)
+    const bool single = tile_mode == 1, resident = tile_mode == 2;
     constexpr int GIBBS_LIST = gibbs_list_len<NS>();
     if (!CL) { crank = 0; csize = 1; }
     const int gnb = csize * nb;        // blocks of 32 draws per round, over the whole cluster
@@ -206,9 +211,7 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
     int* const cnt = gs.cnt;
     const int smem_S = gs.row_S;
     const size_t buf_doubles = (size_t)nb * S * 32;  // one round's tiles: the second buffer starts right behind
-    // `single`: one tile buffer instead of two -- a level of many strains then still runs many blocks per round; the tiles
-    // of the next round are fetched when the round is over (the copy is exposed, but the round is twice as wide)
-    const bool staged = STAGED_ONLY || (single ? 1 : 2) * buf_doubles <= gs.wbuf_doubles;
+    const bool staged = STAGED_ONLY || resident || (single ? 1 : 2) * buf_doubles <= gs.wbuf_doubles;
     const int tid = threadIdx.x, lane = tid & 31, b = tid >> 5;
     const unsigned full = 0xffffffffu;
     const int Dp = padded_draws(D);
@@ -250,7 +253,22 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
             }
         }
     };
-    if (my_rounds > 0) stage(0);
+    if (resident)
+    {
+        if (my_rounds > 0)
+        {
+            if (tid == 0)
+            {
+                const unsigned bytes = (unsigned)tiles * (unsigned)S * 256u;
+                mbar_expect_tx(&bars[0], bytes);
+                for (unsigned o = 0; o < bytes; o += 65536u)
+                    bulk_g2s(reinterpret_cast<char*>(wbuf) + o, reinterpret_cast<const char*>(wt) + o, min(65536u, bytes - o), &bars[0]);
+            }
+            mbar_wait(&bars[0], uses0 & 1u);
+            uses0 += 1;
+        }
+    }
+    else if (my_rounds > 0) stage(0);
     const int Cs = (S + GIBBS_NW - 1) / GIBBS_NW;    // strains per chunk
     const unsigned long long below = (b == 0) ? 0ull : (~0ull >> (64 - 8 * b));  // the bytes of hpack that precede this block
     const unsigned below_lo = (unsigned)below, below_hi = (unsigned)(below >> 32);
@@ -284,7 +302,7 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
         const int cd = cd_next;
         if (r + 1 < n_rounds)
         {
-            if (!single && r + 1 < my_rounds) stage(r + 1);  // overlaps this round's arithmetic
+            if (!single && !resident && r + 1 < my_rounds) stage(r + 1);  // overlaps this round's arithmetic
             t_next += gnb;
             while (t_next >= tiles) { t_next -= tiles; ++sw_next; }
             const int dn = t_next * 32 + lane;
@@ -292,14 +310,15 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
             u_next = vn ? U[(long long)sw_next * D + dn] : 0.0;
             cd_next = (vn && count_letters) ? code[dn] : 0;
         }
-        if (staged && r < my_rounds)
+        if (staged && !resident && r < my_rounds)
         {
             if (single) mbar_wait(&bars[0], (uses0 + (unsigned)r) & 1u);
             else mbar_wait(&bars[r & 1], (((r & 1) ? uses1 : uses0) + (unsigned)(r >> 1)) & 1u);
         }
         unsigned long long* hpack = hpacks + (r & 1) * smem_S;
         unsigned char* hbytes = reinterpret_cast<unsigned char*>(hpack);
-        const double* wl = staged ? wbuf + (size_t)(single ? 0 : (r & 1)) * buf_doubles + (size_t)b * S * 32 + lane
+        const double* wl = resident ? wbuf + (size_t)t_cur * S * 32 + lane
+                         : staged ? wbuf + (size_t)(single ? 0 : (r & 1)) * buf_doubles + (size_t)b * S * 32 + lane
                                   : wt + (long long)t_cur * S * 32 + lane;
         double off[GIBBS_NW + 1];
         off[0] = 0;
@@ -611,7 +630,7 @@ __device__ __forceinline__ void gibbs_w_chain(const GibbsShared& gs, unsigned& u
                 if (cnt[k]) dsmem_add_u32(dsmem_addr(cnt + k, 0u), (unsigned)cnt[k]);
         cluster_barrier();
     }
-    if (staged)
+    if (staged && !resident)
     {
         if (single) uses0 += (unsigned)my_rounds;
         else

@@ -1236,7 +1236,7 @@ struct Engine
         if (forced_tile > 0) tile = forced_tile;
         WalkParams wp;
         wp.n = prm.n;
-        wp.single_buffer = getenv("RAMBL_WALK_DOUBLE") ? 0 : 1;
+        wp.single_buffer = getenv("RAMBL_WALK_TILES") ? atoi(getenv("RAMBL_WALK_TILES")) : 3;
         wp.tau = tau;
         wp.uniforms = d_U.p;
         wp.counters = d_counters.p;

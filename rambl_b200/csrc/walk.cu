@@ -498,10 +498,12 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
                 const int nb_one = (int)min((size_t)NB, gs.wbuf_doubles / ((size_t)S * 32));
                 // a wide level: one tile buffer instead of two when that buys at least half as many blocks again
                 const bool single = prm.single_buffer && nb_two < NB && 2 * nb_one >= 3 * max(nb_two, 1);
-                int nb = single ? nb_one : nb_two;
+                // ... and when the weights of the whole level fit, they are copied once and stay (all NB blocks per round)
+                const bool resident = (prm.single_buffer & 2) && (size_t)padded_draws(D) * S <= gs.wbuf_doubles;
+                int nb = resident ? NB : (single ? nb_one : nb_two);
                 if (nb == 0) nb = NB;
                 gibbs_w_chain<NB, NS, false, CL>(gs, uses0, uses1, nb, S, D, nsweeps, true, wt, codes, prm.uniforms, ws.ab, rounds, passes,
-                                                 prm.counters, crank, csize, single);
+                                                 prm.counters, crank, csize, resident ? 2 : (single ? 1 : 0));
                 if (warp == 0)
                 {   // normalise the masses; fold the averaged letter counts into the models (lines 217-243)
                     const double* mass = gs.masses;

@@ -105,7 +105,8 @@ struct WalkSub
 struct WalkParams
 {
     int n;          // sweep cap (5000)
-    int single_buffer;  // 1: wide levels may run with one tile buffer (more blocks per round, the tile copy exposed)
+    int single_buffer;  // bit 0: wide levels may run with one tile buffer (more blocks per round, the tile copy exposed);
+                        // bit 1: a level whose weights fit the tile buffers as a whole copies them once and keeps them
     double tau;
     const double* uniforms;               // the std::mt19937(1234) canonical stream
     unsigned long long* counters;         // [0] rounds, [1] passes, [2] rounds that did not settle
