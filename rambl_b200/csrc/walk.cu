@@ -23,8 +23,6 @@ constexpr unsigned long long LEN_MUL = 0x9e3779b97f4a7c15ull;
 
 struct WalkShared  // carved out of dynamic shared memory after the Gibbs arrays
 {
-    double* lut;            // [NB][36] log substitution table of the strain a warp is updating
-    double* comp;           // [NB][8]
     unsigned long long* keys;  // [SMAX]
     double* ab;             // [SMAX] candidate abundances
     double* al;             // [SMAX] increments of this level
@@ -67,7 +65,6 @@ size_t walk_smem_bytes(int nb, int tile_S, bool cluster)
     b += al(sizeof(uint2) * (size_t)nb * (32 * 4 + 8));          // lists (NS = 4)
     b += al(sizeof(unsigned) * (size_t)nb * WALK_SMAX);          // pmask
     b += al(sizeof(int) * WALK_SMAX * 8);                        // cnt
-    b += al(sizeof(double) * (size_t)nb * 36) + al(sizeof(double) * (size_t)nb * 8);
     b += al(sizeof(unsigned long long) * WALK_SMAX);
     b += 3 * al(sizeof(double) * WALK_SMAX);
     b += 5 * al(sizeof(int) * WALK_SMAX);
@@ -112,8 +109,6 @@ __global__ void __launch_bounds__(32 * NB, (NB >= 8 ? 1 : 12 / NB)) k_walk(const
         gs.cflag = carve<unsigned>(sp, 2 * GIBBS_CMAX);
     }
     WalkShared ws;
-    ws.lut = carve<double>(sp, (size_t)NB * 36);
-    ws.comp = carve<double>(sp, (size_t)NB * 8);
     ws.keys = carve<unsigned long long>(sp, WALK_SMAX);
     ws.ab = carve<double>(sp, WALK_SMAX);
     ws.al = carve<double>(sp, WALK_SMAX);
