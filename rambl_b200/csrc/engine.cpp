@@ -1046,7 +1046,7 @@ struct Engine
             scr(p.d_ops, sizeof(int2) * WALK_KMAX);
             scr(p.d_kid, sizeof(double) * WALK_KMAX);
             scr(p.d_lut, sizeof(double) * WALK_SMAX * 36);
-            scr(p.d_helper, sizeof(int) * 4);
+            scr(p.d_helper, sizeof(int) * 8);
             scr(p.d_paths, sizeof(int) * (size_t)WALK_SMAX * p.n_levels);
         }
         if (getenv("RAMBL_TRACE") && take.size() < n)

@@ -1,8 +1,8 @@
 // The device-resident strain walk for sm_100a (see walk.cuh for what it replaces and why).
 //
-// One CTA of NB warps owns one subgroup from "^" to "$".  Every phase of a level is a loop over the CTA's threads
-// with CTA barriers in between; the Gibbs sweeps are gibbs_w_chain (dpm_dev.cuh), the same code the level-synchronous
-// kernel k_gibbs_w runs, with NB 32-draw blocks per round; the bookkeeping between levels (pruning, path extension,
+// One CTA of NB warps -- or a cluster of such CTAs -- owns one subgroup from "^" to "$".  Every phase of a level is a loop
+// over the threads of the CTA(s) with barriers in between; the Gibbs sweeps are gibbs_w_chain (dpm_dev.cuh), the same code
+// the level-synchronous kernel k_gibbs_w runs, with up to NB 32-draw blocks per CTA and round; the bookkeeping between levels (pruning, path extension,
 // the 80-candidate cut, slot assignment) is done by warp 0 with ballots and scans, in the order the reference's loops
 // visit candidates and edges, because strain order, tie-breaking and the floating-point sums depend on that order.
 // Everything a level reads from the host side is static (uploaded once); nothing goes back until the walk ends.

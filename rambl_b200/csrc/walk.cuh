@@ -11,6 +11,8 @@
 // waits for its slowest subgroup.  Here a subgroup's levels are a loop inside its CTA; the level tables are
 // uploaded once (the level structure is a property of the graph, not of the candidate strains), subgroups advance
 // independently, and the host only closes the result ("$": sort + merge_strains) and runs read_assign.
+// A batch with fewer subgroups than SMs gives each subgroup a thread-block CLUSTER: the phases of a level are split over
+// all its CTAs and the Gibbs chain runs over distributed shared memory (dpm_dev.cuh).
 // Subgroups the kernel cannot take (see WALK_* below) are solved by the level-synchronous path instead.
 #pragma once
 #include <cuda_runtime.h>
@@ -94,7 +96,8 @@ struct WalkSub
     int2* ops;                      // [WALK_KMAX] slot copies queued by the last extension
     double* kid_ab;                 // [WALK_KMAX] scratch of the cut
     double* lut;                    // [WALK_SMAX][36] log substitution tables of the level's strains
-    int* helper;                    // [4] cluster launches: what rank 0 tells the helper CTAs (0 = the walk is over | 1, S, D, sweeps)
+    int* helper;                    // [8] cluster launches: the level descriptor rank 0 publishes (candidates, candidate buffer,
+                                    // slot copies, branching flag, stop code or -1)
     // ---- result
     WalkResult* res;
     int* paths;                     // [<= WALK_SMAX][n_levels] node ids of the final candidates' paths
