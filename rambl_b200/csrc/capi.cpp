@@ -588,7 +588,12 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
         bool fresh = b->threaded_upto == 0 && b->msa.problems() == 0;
         for (auto& sp : b->subs) fresh = fresh && !sp->built;
         // small batches gain nothing from chunks (their chains are latency-bound and get clusters instead)
-        const size_t n_chunks = N >= 192 ? 4 : (N >= 96 ? 2 : 1);
+        size_t n_chunks = N >= 192 ? 4 : (N >= 96 ? 2 : 1);
+        size_t n_drivers = 2;
+        if (const char* ev = getenv("RAMBL_SOLVE_CHUNKS")) n_chunks = std::max(1, atoi(ev));
+        if (const char* ev = getenv("RAMBL_SOLVE_DRIVERS")) n_drivers = std::max(1, atoi(ev));
+        n_chunks = std::min(n_chunks, std::max<size_t>(N, 1));
+        n_drivers = std::min(n_drivers, n_chunks);
         if (!fresh || n_chunks == 1)
         {   // nothing to overlap (or a batch that is partly built already): the two calls, one after the other
             int rc = rambl_batch_build_graphs(b);
@@ -599,6 +604,7 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
         }
         InferParams prm;
         prm.n = n; prm.e = e; prm.tau = tau; prm.diff = diff; prm.assign = do_assign != 0; prm.keep_loglik = keep_loglik != 0;
+        prm.max_cluster = 1;  // the kernels of consecutive chunks share the SMs: one CTA per subgroup
         int device = 0;
         RAMBL_CUDA(cudaGetDevice(&device));
         std::atomic<size_t> next(0);
@@ -693,9 +699,10 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
             }
             if (st) cudaStreamDestroy(st);
         };
-        std::thread second(drive);
+        std::vector<std::thread> others;
+        for (size_t t = 1; t < n_drivers; ++t) others.emplace_back(drive);
         drive();
-        second.join();
+        for (std::thread& t : others) t.join();
         b->threaded_upto = N;
         b->msa = MsaBatch();
         b->last = prm;

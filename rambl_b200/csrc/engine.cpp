@@ -1230,6 +1230,7 @@ struct Engine
             if (take.size() <= 16) cluster = 8;
             else if (take.size() <= 32) cluster = 4;
             else if (take.size() <= 72) cluster = 2;
+            if (prm.max_cluster > 0) cluster = std::min(cluster, prm.max_cluster);
             if (forced_cluster > 0) cluster = forced_cluster;
         }
         while (tile + 4 <= WALK_SMAX && walk_smem_bytes(nb, tile + 4, cluster > 1) <= sm_bytes) tile += 4;

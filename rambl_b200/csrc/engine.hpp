@@ -24,6 +24,7 @@ struct InferParams
     float diff = 0.01f;   // --diff-rate
     bool assign = true;   // run read_assign and the final sort
     bool keep_loglik = false;  // also return the per-read log-likelihood rows of the inferred strains
+    int max_cluster = 0;  // > 0: at most this many CTAs per subgroup in the walk (the overlapped solve runs several chunks' kernels side by side)
     bool level_synchronous = false;  // this call: the level-synchronous path only (the side batch of subgroups the walk cannot take)
 };
 
