@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 #include <map>
 #include <queue>
 #include <set>
@@ -89,13 +90,21 @@ struct PoolItem
     }
 };
 
+// A vertex's read pool has one of two forms.  Nearly every entry of a graph belongs to a match / mismatch node, which
+// a read enters at most once, with the node's own letter and the read's copy number: such a pool is just the ascending
+// list of read ids (`rids`, 4 bytes per entry instead of a 32-byte PoolItem) -- the "plain" form.  Anything else
+// (per-read insertion / deletion nodes, merged or collapsed nodes) keeps explicit items in `pool`.  A plain pool is
+// turned into items the moment something needs them (Impl::itemise).
 struct Vertex
 {
     uint8_t st = ST_MAT;
     bool alive = true;
+    bool plain = false;     // the pool is `rids` x (`letter`, copies of the read); `pool` is empty
+    char letter = 0;
     std::string label;
     int level = -1;
     std::vector<int> out, in, sib;
+    std::vector<int> rids;
     std::vector<PoolItem> pool;
 };
 
@@ -129,6 +138,7 @@ struct GraphBuilder::Impl
     std::vector<LevelPlan> plans;
     int first_problem = 0, n_problems = 0;
     int n_reads = 0;
+    std::vector<int> copies;  // per read id (every pool entry of a read carries the read's copy number)
     // Guard against inputs on which the reference's construction never ends (alignments that make the
     // graph cyclic, e.g. reads that begin with a deletion): every loop below pays into one budget.
     mutable long long work = 0;
@@ -146,6 +156,25 @@ struct GraphBuilder::Impl
         return (int)V.size() - 1;
     }
     int add(uint8_t st, char c) { return add(st, std::string(1, c)); }
+    // a node whose pool will be in the plain form
+    int add_plain(uint8_t st, char c)
+    {
+        const int h = add(st, std::string(1, c));
+        V[h].plain = true;
+        V[h].letter = c;
+        return h;
+    }
+    size_t pool_size(int h) const { return V[h].plain ? V[h].rids.size() : V[h].pool.size(); }
+    int pool_front(int h) const { return V[h].plain ? V[h].rids[0] : V[h].pool[0].rid; }  // read id of the first entry
+    void itemise(int h)
+    {
+        Vertex& x = V[h];
+        if (!x.plain) return;
+        x.pool.reserve(x.rids.size());
+        for (int rid : x.rids) x.pool.push_back({rid, PoolStr(x.letter), copies[rid]});
+        std::vector<int>().swap(x.rids);
+        x.plain = false;
+    }
     bool has_edge(int u, int v) const
     {
         for (int o : V[u].out) if (o == v) return true;
@@ -188,7 +217,24 @@ struct GraphBuilder::Impl
             const std::vector<int> vout = V[v].out;
             for (int y : vout) if (y != u && !has_edge(u, y)) connect(u, y);
         }
-        if (has_edge(u, v) && V[u].st == ST_MAT && V[v].st == ST_MAT) V[u].label += V[v].label;
+        const bool chained = has_edge(u, v) && V[u].st == ST_MAT && V[v].st == ST_MAT;
+        if (chained) V[u].label += V[v].label;
+        if (!chained && V[u].plain && V[v].plain && V[u].letter == V[v].letter)
+        {
+            // two plain pools with the same letter and no read in common stay plain: the union of the ids
+            std::vector<int>& ra = V[u].rids;
+            const std::vector<int>& rb = V[v].rids;
+            std::vector<int> r(ra.size() + rb.size());
+            const auto end = std::set_union(ra.begin(), ra.end(), rb.begin(), rb.end(), r.begin());
+            if ((size_t)(end - r.begin()) == ra.size() + rb.size())
+            {
+                ra.swap(r);
+                drop(v, false);
+                return;
+            }
+        }
+        itemise(u);
+        itemise(v);
         std::vector<PoolItem>& a = V[u].pool;
         std::vector<PoolItem>& b = V[v].pool;
         std::sort(a.begin(), a.end());
@@ -216,8 +262,10 @@ struct GraphBuilder::Impl
         V.reserve(G.size() + 2 + R.size());
         backbone = (int)G.size();
         n_reads = (int)R.size();
+        copies.resize(R.size());
+        for (size_t rid = 0; rid < R.size(); ++rid) copies[rid] = R[rid].cn;
         int u = add(ST_MAT, '^');
-        for (char c : G) { int w = add(ST_MAT, c); connect(u, w); u = w; }
+        for (char c : G) { int w = add_plain(ST_MAT, c); connect(u, w); u = w; }
         connect(u, add(ST_MAT, '$'));
         const int last = backbone + 1;
         {
@@ -235,7 +283,7 @@ struct GraphBuilder::Impl
             for (size_t i = 0; i < G.size(); ++i)
             {
                 depth += cover[i];
-                if (depth > 0) V[i + 1].pool.reserve((size_t)depth);
+                if (depth > 0) V[i + 1].rids.reserve((size_t)depth);
             }
         }
 
@@ -277,12 +325,12 @@ struct GraphBuilder::Impl
                                 if (V[s].st == st && V[s].label[0] == r[j]) { hit = s; break; }
                         if (hit < 0)
                         {
-                            hit = add(st, r[j]);
+                            hit = add_plain(st, r[j]);
                             connect(u, hit);
                             V[v].sib.push_back(hit);
                         }
                         else if (!has_edge(u, hit)) connect(u, hit);
-                        V[hit].pool.push_back({rid, PoolStr(r[j]), rd.cn});
+                        V[hit].rids.push_back(rid);  // a read passes a column once: ids stay ascending
                         u = hit;
                         step_v();
                     }
@@ -293,8 +341,8 @@ struct GraphBuilder::Impl
                     std::vector<int> chain;
                     for (int q = 0; q < len; ++q, ++j)
                     {
-                        int w = add(ST_INS, r[j]);
-                        V[w].pool.push_back({rid, PoolStr(r[j]), rd.cn});
+                        int w = add_plain(ST_INS, r[j]);
+                        V[w].rids.push_back(rid);
                         chain.push_back(w);
                     }
                     if (chain.empty()) continue;
@@ -306,8 +354,8 @@ struct GraphBuilder::Impl
                     std::vector<int> chain;
                     for (int q = 0; q < len; ++q)
                     {
-                        int w = add(ST_DEL, '=');
-                        V[w].pool.push_back({rid, "=", rd.cn});
+                        int w = add_plain(ST_DEL, '=');
+                        V[w].rids.push_back(rid);
                         chain.push_back(w);
                         step_v();
                     }
@@ -388,17 +436,28 @@ struct GraphBuilder::Impl
     // find_common_read_pool, PartialOrderGraph.cpp:780-829 -> (rid, cn) in set order
     std::vector<std::pair<int, int>> shared_reads(int a, int b) const
     {
-        std::set<std::pair<int, int>> ra, rb;
-        for (const PoolItem& p : V[a].pool) ra.insert({p.rid, p.cn});
-        for (int o : V[a].out)
-            if (V[o].st == ST_INS || V[o].st == ST_DEL)
-                for (const PoolItem& p : V[o].pool) ra.erase({p.rid, p.cn});
-        for (const PoolItem& p : V[b].pool) rb.insert({p.rid, p.cn});
-        for (int o : V[b].in)
-            if (V[o].st == ST_INS || V[o].st == ST_DEL)
-                for (const PoolItem& p : V[o].pool) rb.erase({p.rid, p.cn});
-        std::vector<std::pair<int, int>> c;
-        for (const auto& x : ra) if (rb.count(x)) c.push_back(x);
+        typedef std::vector<std::pair<int, int>> Pairs;
+        auto list = [&](int h, Pairs& to) {
+            const Vertex& x = V[h];
+            if (x.plain) for (int rid : x.rids) to.push_back({rid, copies[rid]});
+            else for (const PoolItem& p : x.pool) to.push_back({p.rid, p.cn});
+        };
+        // the (rid, cn) set of node h without those of its insertion / deletion neighbours on one side, ascending
+        auto own = [&](int h, const std::vector<int>& nb) {
+            Pairs all, gone, left;
+            list(h, all);
+            for (int o : nb)
+                if (V[o].st == ST_INS || V[o].st == ST_DEL) list(o, gone);
+            std::sort(all.begin(), all.end());
+            all.erase(std::unique(all.begin(), all.end()), all.end());
+            if (gone.empty()) return all;
+            std::sort(gone.begin(), gone.end());
+            std::set_difference(all.begin(), all.end(), gone.begin(), gone.end(), std::back_inserter(left));
+            return left;
+        };
+        const Pairs ra = own(a, V[a].out), rb = own(b, V[b].in);
+        Pairs c;
+        std::set_intersection(ra.begin(), ra.end(), rb.begin(), rb.end(), std::back_inserter(c));
         return c;
     }
 
@@ -424,18 +483,17 @@ struct GraphBuilder::Impl
             {
                 const std::string aligned = rows.row(lp.problem, (int)t);
                 if (aligned == lp.seqs[t]) continue;
-                int rid = 0, rcn = 0;
+                int rid = 0;
                 for (int h : lp.spans[t].chain)
                 {
-                    rid = V[h].pool[0].rid;
-                    rcn = V[h].pool[0].cn;
+                    rid = pool_front(h);
                     drop(h, true);
                 }
                 std::vector<int> chain;
                 for (char c : aligned)
                 {
-                    int w = add(ST_INS, c);
-                    V[w].pool.push_back({rid, PoolStr(c), rcn});
+                    int w = add_plain(ST_INS, c);
+                    V[w].rids.push_back(rid);
                     chain.push_back(w);
                 }
                 hang(lp.spans[t].from, lp.spans[t].to, chain);
@@ -450,9 +508,10 @@ struct GraphBuilder::Impl
             std::vector<int> chain;
             for (int t = 0; t < width; ++t)
             {
-                int w = add(ST_INS, '-');
-                V[w].pool.reserve(crp.size());
-                for (const auto& r : crp) V[w].pool.push_back({r.first, "-", r.second});
+                // the shared reads come in ascending id order, one entry per read, with the read's copies: a plain pool
+                int w = add_plain(ST_INS, '-');
+                V[w].rids.reserve(crp.size());
+                for (const auto& r : crp) V[w].rids.push_back(r.first);
                 chain.push_back(w);
             }
             hang(e.first, e.second, chain);
@@ -544,12 +603,12 @@ struct GraphBuilder::Impl
                 const int have = (int)d.chain.size();
                 if (want - have <= 0) continue;
                 const int first = d.chain[0];
-                const int rid = V[first].pool[0].rid, rcn = V[first].pool[0].cn;
+                const int rid = pool_front(first);
                 std::vector<int> chain;
                 for (int t = want - have; t > 0; --t)
                 {
-                    int w = add(ST_DEL, '=');
-                    V[w].pool.push_back({rid, "=", rcn});
+                    int w = add_plain(ST_DEL, '=');
+                    V[w].rids.push_back(rid);
                     chain.push_back(w);
                 }
                 hang(d.from, first, chain);
@@ -679,7 +738,9 @@ struct GraphBuilder::Impl
             const Vertex& x = V[h];
             if (!x.alive) continue;
             id[h] = N++;
-            n_pool += x.pool.size(); n_out += x.out.size(); n_in += x.in.size(); n_label += x.label.size();
+            n_out += x.out.size(); n_in += x.in.size(); n_label += x.label.size();
+            if (x.plain) { n_pool += x.rids.size(); n_pool_chars += x.rids.size(); continue; }
+            n_pool += x.pool.size();
             for (size_t k = 0; k < x.pool.size(); ++k)
             {
                 n_pool_chars += x.pool[k].s.size();
@@ -694,10 +755,11 @@ struct GraphBuilder::Impl
         g.out_to.reserve(n_out); g.out_cover.reserve(n_out); g.out_off.reserve(N + 1);
         g.in_from.reserve(n_in); g.in_off.reserve(N + 1);
         g.pool_rid.resize(n_pool); g.pool_cn.resize(n_pool); g.pool_off.reserve(N + 1);
-        g.pool_chars.resize(n_pool_chars); g.pool_str_off.assign(n_pool + 1, 0);
+        g.pool_chars.resize(n_pool_chars); g.pool_str_off.resize(n_pool + 1);
+        g.pool_str_off[0] = 0;
         g.label_off.assign(1, 0); g.out_off.assign(1, 0); g.in_off.assign(1, 0); g.pool_off.assign(1, 0);
         size_t at_pool = 0, at_chars = 0;
-        std::vector<int> ids;  // the read ids of the current vertex, ascending
+        std::vector<int> ids;  // the read ids of the current vertex, ascending (when its pool is not plain)
         for (size_t h = 0; h < V.size(); ++h)
         {
             const Vertex& x = V[h];
@@ -707,48 +769,103 @@ struct GraphBuilder::Impl
             g.label_chars.insert(g.label_chars.end(), x.label.begin(), x.label.end());
             g.label_off.push_back((int)g.label_chars.size());
             if (x.label == "$") g.end_node = id[h];
-            if (!x.out.empty())
+            const int* a = x.rids.data();
+            size_t na = x.rids.size();
+            if (!x.out.empty() && !x.plain)
             {
                 ids.clear();
                 for (const PoolItem& p : x.pool) ids.push_back(p.rid);
                 if (!in_read_order[h]) std::sort(ids.begin(), ids.end());
+                a = ids.data();
+                na = ids.size();
             }
             for (int o : x.out)
             {
                 g.out_to.push_back(id[o]);
-                g.out_cover.push_back(reads_over_edge((int)h, o, ids, in_read_order[o] != 0));
+                g.out_cover.push_back(reads_over_edge((int)h, o, a, na, in_read_order[o] != 0));
             }
             g.out_off.push_back((int)g.out_to.size());
             for (int o : x.in) g.in_from.push_back(id[o]);
             g.in_off.push_back((int)g.in_from.size());
-            for (const PoolItem& p : x.pool)
+            if (x.plain)
             {
-                g.pool_rid[at_pool] = p.rid;
-                g.pool_cn[at_pool] = p.cn;
-                const size_t len = p.s.size();
-                if (len == 1) g.pool_chars[at_chars] = p.s[0];
-                else memcpy(g.pool_chars.data() + at_chars, p.s.data(), len);
-                at_chars += len;
-                g.pool_str_off[++at_pool] = (int)at_chars;
+                const size_t n = x.rids.size();
+                if (n)
+                {
+                    memcpy(g.pool_rid.data() + at_pool, x.rids.data(), n * sizeof(int));
+                    memset(g.pool_chars.data() + at_chars, x.letter, n);
+                }
+                int* cn = g.pool_cn.data() + at_pool;
+                int* so = g.pool_str_off.data() + at_pool + 1;
+                for (size_t k = 0; k < n; ++k) { cn[k] = copies[x.rids[k]]; so[k] = (int)(at_chars + k + 1); }
+                at_pool += n;
+                at_chars += n;
             }
+            else
+                for (const PoolItem& p : x.pool)
+                {
+                    g.pool_rid[at_pool] = p.rid;
+                    g.pool_cn[at_pool] = p.cn;
+                    const size_t len = p.s.size();
+                    if (len == 1) g.pool_chars[at_chars] = p.s[0];
+                    else memcpy(g.pool_chars.data() + at_chars, p.s.data(), len);
+                    at_chars += len;
+                    g.pool_str_off[++at_pool] = (int)at_chars;
+                }
             g.pool_off.push_back((int)at_pool);
         }
     }
 
     // number_of_reads_cover_nodes, PartialOrderGraph.cpp:1218-1244: sum over pairs with equal read id of
-    // the second pool's copy number.  `a` holds the first pool's ids in ascending order; a second pool that is
-    // in read order too is merged against it in one pass, any other is looked up item by item.
-    int reads_over_edge(int hu, int hv, const std::vector<int>& a, bool v_in_read_order) const
+    // the second pool's copy number.  `a[0..na)` holds the first pool's ids in ascending order.  Two plain pools are
+    // intersected from the shorter side when one is much shorter (a mismatch node next to a backbone node), else merged
+    // in one pass; a second pool with explicit items is merged if it is in read order and looked up item by item if not.
+    int reads_over_edge(int hu, int hv, const int* a, size_t na, bool v_in_read_order) const
     {
         const Vertex& u = V[hu];
         const Vertex& v = V[hv];
         int n = 0;
-        if (hu == 0) { for (const PoolItem& p : v.pool) n += p.cn; return n; }
-        if (v.label == "$") { for (const PoolItem& p : u.pool) n += p.cn; return n; }
+        if (hu == 0 || v.label == "$")
+        {
+            const Vertex& w = hu == 0 ? v : u;
+            if (w.plain) for (int rid : w.rids) n += copies[rid];
+            else for (const PoolItem& p : w.pool) n += p.cn;
+            return n;
+        }
+        if (v.plain)
+        {
+            const int* b = v.rids.data();
+            const size_t nb = v.rids.size();
+            if (nb * 8 < na)
+            {
+                for (size_t k = 0; k < nb; ++k)
+                {
+                    auto range = std::equal_range(a, a + na, b[k]);
+                    n += (int)(range.second - range.first) * copies[b[k]];
+                }
+                return n;
+            }
+            if (na * 8 < nb)
+            {
+                for (size_t k = 0; k < na; ++k)  // repeated ids in a: each occurrence counts
+                    if (std::binary_search(b, b + nb, a[k])) n += copies[a[k]];
+                return n;
+            }
+            size_t i = 0;
+            for (size_t k = 0; k < nb; ++k)
+            {
+                const int rid = b[k];
+                while (i < na && a[i] < rid) ++i;
+                size_t j = i;
+                while (j < na && a[j] == rid) ++j;
+                n += (int)(j - i) * copies[rid];
+                i = j;  // ids of a plain pool are distinct
+            }
+            return n;
+        }
         if (v_in_read_order)
         {
             size_t i = 0;
-            const size_t na = a.size();
             for (const PoolItem& p : v.pool)
             {
                 while (i < na && a[i] < p.rid) ++i;
@@ -760,7 +877,7 @@ struct GraphBuilder::Impl
         }
         for (const PoolItem& p : v.pool)
         {
-            auto range = std::equal_range(a.begin(), a.end(), p.rid);
+            auto range = std::equal_range(a, a + na, p.rid);
             n += (int)(range.second - range.first) * p.cn;
         }
         return n;

@@ -39,3 +39,29 @@ def test_bench_workload_definitions_match_the_golden_specs():
     assert c["spec"] == dict(n_reads=5000, read_len=150, n_strains=2 + 3 % 5, seed=3)
     sg = synth.config2_subgroup(3)
     assert sg.seq == c["input"]["seq"] and sg.pos == c["input"]["pos"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_graph_construction_at_full_size_equals_the_reference(name):
+    """The host half of graph construction (pog.cpp) at benchmark size, with the insertion rows supplied by the oracle's
+    alignment: node dump and output_edge text hash to what the unmodified reference produced (the GPU parity test repeats
+    this with the rows from the device kernel)."""
+    import hashlib
+    from helpers import strip_sib
+    from oracle import refpy
+    from rambl_b200 import api
+    case = load_golden_gz("full_%s.json.gz" % name)
+    inp = case["input"]
+    spec = dict(case["spec"])
+    if "divergence" in spec:
+        spec["divergence"] = tuple(spec["divergence"])
+    sg = synth.make_subgroup(**spec)
+    assert sg.seq == inp["seq"]
+    b = api.StrainCallBatch()
+    b.add(sg)
+    b.thread_reads()
+    b.finish_graphs_with_rows([refpy.msa_align(p, "oracle") for p in b.msa_problems()])
+    assert b.num_nodes(0) == case["n_nodes"]
+    assert hashlib.sha256(strip_sib(b.graph_dump(0)).encode()).hexdigest() == case["dump_nosib_sha256"]
+    assert hashlib.sha256(b.output_edge(0).encode()).hexdigest() == case["edges_sha256"]
+    b.close()
