@@ -57,7 +57,7 @@ std::string fmt(double x)
 struct Subgroup
 {
     std::string gene;
-    std::vector<AlignedRead> reads;
+    ReadSet reads;
     SubgroupInput input;
     std::unique_ptr<GraphBuilder> builder;
     FlatGraph graph;
@@ -309,11 +309,11 @@ int rambl_batch_add_subgroup(rambl_batch* b, const char* gene, int32_t n_reads, 
             throw Error(RAMBL_ERR_INVALID, "null argument");
         std::unique_ptr<Subgroup> s(new Subgroup);
         s->gene = gene;
-        s->reads.reserve(n_reads);
         for (int i = 0; i < n_reads; ++i)
         {
             if (copies[i] < 1) throw Error(RAMBL_ERR_INVALID, "copy number must be >= 1");
-            s->reads.push_back({pos[i], cigar[i], seq[i], copies[i]});
+            if (!cigar[i] || !seq[i]) throw Error(RAMBL_ERR_INVALID, "null read string");
+            s->reads.add(pos[i], cigar[i], strlen(cigar[i]), seq[i], strlen(seq[i]), copies[i]);
             s->input.read_cn.push_back(copies[i]);
         }
         if (pair_off && pair_val)
@@ -347,15 +347,26 @@ int rambl_batch_add_subgroup_packed(rambl_batch* b, const char* gene, int32_t n_
             throw Error(RAMBL_ERR_INVALID, "null argument");
         std::unique_ptr<Subgroup> s(new Subgroup);
         s->gene = gene;
-        s->reads.reserve(n_reads);
-        s->input.read_cn.reserve(n_reads);
         for (int i = 0; i < n_reads; ++i)
         {
             if (copies[i] < 1) throw Error(RAMBL_ERR_INVALID, "copy number must be >= 1");
             if (cigar_off[i + 1] < cigar_off[i] || seq_off[i + 1] < seq_off[i]) throw Error(RAMBL_ERR_INVALID, "string offsets must not decrease");
-            s->reads.push_back({pos[i], std::string(cigar_chars + cigar_off[i], cigar_chars + cigar_off[i + 1]),
-                                std::string(seq_chars + seq_off[i], seq_chars + seq_off[i + 1]), copies[i]});
-            s->input.read_cn.push_back(copies[i]);
+        }
+        if (n_reads > 0 && (cigar_off[0] < 0 || seq_off[0] < 0)) throw Error(RAMBL_ERR_INVALID, "string offsets must not be negative");
+        {   // the arenas are taken over as they are (offsets rebased to the first read's)
+            ReadSet& rs = s->reads;
+            rs.pos.assign(pos, pos + n_reads);
+            rs.cn.assign(copies, copies + n_reads);
+            s->input.read_cn.assign(copies, copies + n_reads);
+            rs.cigar_off.resize((size_t)n_reads + 1);
+            rs.seq_off.resize((size_t)n_reads + 1);
+            const int64_t c0 = n_reads ? cigar_off[0] : 0, s0 = n_reads ? seq_off[0] : 0;
+            for (int i = 0; i <= n_reads && n_reads; ++i) { rs.cigar_off[i] = cigar_off[i] - c0; rs.seq_off[i] = seq_off[i] - s0; }
+            if (n_reads)
+            {
+                rs.cigar_chars.assign(cigar_chars + c0, cigar_chars + cigar_off[n_reads]);
+                rs.seq_chars.assign(seq_chars + s0, seq_chars + seq_off[n_reads]);
+            }
         }
         if (pair_off && pair_val)
         {
@@ -410,7 +421,7 @@ int rambl_batch_add_graph(rambl_batch* b, int32_t n_nodes, int32_t n_reads, cons
             g.pool_chars.assign(pool_chars, pool_chars + pool_str_off[ne]);
         }
         else g.pool_str_off.assign(1, 0);
-        auto monotone = [&](const std::vector<int>& off, const char* what) {
+        auto monotone = [&](const auto& off, const char* what) {
             if (off[0] != 0) throw Error(RAMBL_ERR_INVALID, std::string(what) + " must start at 0");
             for (size_t i = 1; i < off.size(); ++i)
                 if (off[i] < off[i - 1]) throw Error(RAMBL_ERR_INVALID, std::string(what) + " must not decrease");

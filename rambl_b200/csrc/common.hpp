@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace rambl {
@@ -38,6 +39,33 @@ void cached_device_free(void* p, size_t granted);
 void* cached_pinned_alloc(size_t bytes, size_t* granted);
 void cached_pinned_free(void* p, size_t granted);
 void release_cached_memory();
+
+// Pageable host memory for the large per-subgroup arrays (the read pools of a flat graph: ~9 MB per 5 000-read subgroup).
+// Fresh pages cost a fault each -- measured here at a fifth of graph construction, more when 16 workers fault at
+// once -- so blocks of 64 KB and more are kept when released and handed to the next batch (up to $RAMBL_HOST_CACHE_MB,
+// default 16 384; smaller requests are plain malloc).  release_cached_memory() frees them as well.
+void* cached_host_alloc(size_t bytes);
+void cached_host_free(void* p);
+
+// std::vector allocator over the cache above; elements are default-initialised (resize() does not zero what the caller
+// is about to overwrite).
+template <typename T>
+struct HostCacheAlloc
+{
+    typedef T value_type;
+    HostCacheAlloc() {}
+    template <typename U> HostCacheAlloc(const HostCacheAlloc<U>&) {}
+    T* allocate(size_t n) { return static_cast<T*>(cached_host_alloc(n * sizeof(T))); }
+    void deallocate(T* p, size_t) { cached_host_free(p); }
+    template <typename U> void construct(U* p) { ::new (static_cast<void*>(p)) U; }
+    template <typename U, typename A0, typename... A> void construct(U* p, A0&& a0, A&&... a)
+    {
+        ::new (static_cast<void*>(p)) U(std::forward<A0>(a0), std::forward<A>(a)...);
+    }
+    template <typename U> bool operator==(const HostCacheAlloc<U>&) const { return true; }
+    template <typename U> bool operator!=(const HostCacheAlloc<U>&) const { return false; }
+};
+template <typename T> using HostVec = std::vector<T, HostCacheAlloc<T>>;
 
 // A device buffer that only grows; reused across launches so the level loop does not malloc.
 template <typename T>

@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <new>
 #include <thread>
 
 #include "common.hpp"
@@ -100,16 +101,91 @@ void cached_pinned_free(void* p, size_t granted)
     cache().pinned.insert({granted, p});
 }
 
+// ---- pageable host blocks (common.hpp: cached_host_alloc).  A block carries its capacity in a 64-byte header; a
+// request takes the smallest kept block that is large enough and at most half as large again.
+namespace {
+const size_t kHostHeader = 64, kHostSmall = 64 * 1024;
+struct HostCache
+{
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;  // capacity -> block (header address)
+    size_t held = 0, limit = 0;
+};
+HostCache& host_cache()
+{
+    static HostCache* c = [] {
+        HostCache* h = new HostCache;
+        const char* e = getenv("RAMBL_HOST_CACHE_MB");
+        h->limit = (size_t)(e ? std::max(0L, atol(e)) : 16384L) << 20;
+        return h;
+    }();
+    return *c;
+}
+}  // namespace
+
+void* cached_host_alloc(size_t bytes)
+{
+    if (bytes == 0) bytes = 1;
+    size_t cap = bytes;
+    void* base = nullptr;
+    if (bytes >= kHostSmall)
+    {
+        cap = (bytes + 0xffff) & ~(size_t)0xffff;
+        HostCache& hc = host_cache();
+        std::lock_guard<std::mutex> lk(hc.mu);
+        auto it = hc.free_blocks.lower_bound(cap);
+        if (it != hc.free_blocks.end() && it->first <= cap + cap / 2)
+        {
+            base = it->second;
+            cap = it->first;
+            hc.held -= cap;
+            hc.free_blocks.erase(it);
+        }
+    }
+    if (!base)
+    {
+        base = malloc(kHostHeader + cap);
+        if (!base) throw std::bad_alloc();
+    }
+    *static_cast<size_t*>(base) = cap;
+    return static_cast<char*>(base) + kHostHeader;
+}
+
+void cached_host_free(void* p)
+{
+    if (!p) return;
+    void* base = static_cast<char*>(p) - kHostHeader;
+    const size_t cap = *static_cast<size_t*>(base);
+    if (cap >= kHostSmall)
+    {
+        HostCache& hc = host_cache();
+        std::lock_guard<std::mutex> lk(hc.mu);
+        if (hc.held + cap <= hc.limit)
+        {
+            hc.free_blocks.insert({cap, base});
+            hc.held += cap;
+            return;
+        }
+    }
+    free(base);
+}
+
 void release_cached_memory()
 {
-    std::multimap<size_t, void*> d, h;
+    std::multimap<size_t, void*> d, h, m;
     {
         std::lock_guard<std::mutex> lk(cache().mu);
         d.swap(cache().device);
         h.swap(cache().pinned);
     }
+    {
+        std::lock_guard<std::mutex> lk(host_cache().mu);
+        m.swap(host_cache().free_blocks);
+        host_cache().held = 0;
+    }
     for (auto& kv : d) cudaFree(kv.second);
     for (auto& kv : h) cudaFreeHost(kv.second);
+    for (auto& kv : m) free(kv.second);
 }
 
 }  // namespace rambl

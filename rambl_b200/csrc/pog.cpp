@@ -256,14 +256,14 @@ struct GraphBuilder::Impl
 
     // ---- phase A -------------------------------------------------------------------------------
     // PartialOrderGraph::build up to (not including) canonize_graph, PartialOrderGraph.cpp:67-255
-    void splice_reads(const std::string& G, const std::vector<AlignedRead>& R)
+    void splice_reads(const std::string& G, const ReadSet& R)
     {
         V.clear();
         V.reserve(G.size() + 2 + R.size());
         backbone = (int)G.size();
         n_reads = (int)R.size();
         copies.resize(R.size());
-        for (size_t rid = 0; rid < R.size(); ++rid) copies[rid] = R[rid].cn;
+        for (size_t rid = 0; rid < R.size(); ++rid) copies[rid] = R.cn[rid];
         int u = add(ST_MAT, '^');
         for (char c : G) { int w = add_plain(ST_MAT, c); connect(u, w); u = w; }
         connect(u, add(ST_MAT, '$'));
@@ -272,11 +272,12 @@ struct GraphBuilder::Impl
             // backbone pools grow to the coverage of their position: size them once (difference array over the
             // reads' reference spans) instead of doubling their way up
             std::vector<int> cover(G.size() + 2, 0);
-            for (const AlignedRead& rd : R)
+            for (size_t rid = 0; rid < R.size(); ++rid)
             {
-                if (rd.pos < 0 || rd.pos >= last) continue;  // refused below
-                const int hi = (int)std::min<size_t>(G.size(), (size_t)rd.pos + rd.seq.size());
-                ++cover[rd.pos];
+                const int pos = R.pos[rid];
+                if (pos < 0 || pos >= last) continue;  // refused below
+                const int hi = (int)std::min<size_t>(G.size(), (size_t)pos + R.seq(rid).size());
+                ++cover[pos];
                 --cover[hi];
             }
             int depth = 0;
@@ -289,19 +290,19 @@ struct GraphBuilder::Impl
 
         for (int rid = 0; rid < (int)R.size(); ++rid)
         {
-            const AlignedRead& rd = R[rid];
-            if (rd.pos < 0 || rd.pos >= last) throw Error(RAMBL_ERR_INVALID, "read starts outside the gene window");
-            const std::string& r = rd.seq;
-            int i = rd.pos, j = 0;
-            u = rd.pos;
-            int v = rd.pos + 1;
+            const int pos = R.pos[rid];
+            if (pos < 0 || pos >= last) throw Error(RAMBL_ERR_INVALID, "read starts outside the gene window");
+            const std::string_view r = R.seq(rid);
+            int i = pos, j = 0;
+            u = pos;
+            int v = pos + 1;
             auto step_v = [&]() {
                 ++i;
                 if (i + 1 > last) throw Error(RAMBL_ERR_INVALID, "read runs past the end of the gene window");
                 v = i + 1;
             };
             size_t k = 0;
-            const std::string& cg = rd.cigar;
+            const std::string_view cg = R.cigar(rid);
             while (k < cg.size())
             {
                 int len = 0;
@@ -329,7 +330,7 @@ struct GraphBuilder::Impl
                             connect(u, hit);
                             V[v].sib.push_back(hit);
                         }
-                        else if (!has_edge(u, hit)) connect(u, hit);
+                        else if (!(hit == v && u == v - 1) && !has_edge(u, hit)) connect(u, hit);  // backbone edges are there from the start
                         V[hit].rids.push_back(rid);  // a read passes a column once: ids stay ascending
                         u = hit;
                         step_v();
@@ -894,7 +895,7 @@ void GraphBuilder::rebase_problems(int first)
     m->first_problem = first;
 }
 
-void GraphBuilder::thread(const std::string& gene, const std::vector<AlignedRead>& reads, MsaBatch& batch)
+void GraphBuilder::thread(const std::string& gene, const ReadSet& reads, MsaBatch& batch)
 {
     m->splice_reads(gene, reads);
     m->plan_insertions(batch);

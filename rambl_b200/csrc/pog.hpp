@@ -14,6 +14,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <string_view>
 #include <vector>
 
 #include "msa_sp.hpp"
@@ -22,11 +23,26 @@ namespace rambl {
 
 enum : uint8_t { ST_MAT = 0, ST_MIS = 1, ST_INS = 2, ST_DEL = 3 };  // AlignState, PartialOrderGraph.hpp:82
 
-struct AlignedRead  // AlignRead, PartialOrderGraph.hpp:218 (the quality string is never used)
+// The aligned reads of one subgroup (AlignRead, PartialOrderGraph.hpp:218; the quality string is never used): positions
+// and copy numbers as arrays, CIGARs and letters as two byte arenas with offsets -- the layout the packed C-ABI call
+// hands over, so that adding a subgroup is a handful of block copies instead of two strings per read.
+struct ReadSet
 {
-    int pos;
-    std::string cigar, seq;
-    int cn;
+    std::vector<int> pos, cn;
+    std::vector<int64_t> cigar_off{0}, seq_off{0};
+    std::vector<char> cigar_chars, seq_chars;
+    size_t size() const { return pos.size(); }
+    std::string_view cigar(size_t i) const { return std::string_view(cigar_chars.data() + cigar_off[i], (size_t)(cigar_off[i + 1] - cigar_off[i])); }
+    std::string_view seq(size_t i) const { return std::string_view(seq_chars.data() + seq_off[i], (size_t)(seq_off[i + 1] - seq_off[i])); }
+    void add(int p, const char* cigar_text, size_t cigar_len, const char* letters, size_t n_letters, int copies)
+    {
+        pos.push_back(p);
+        cn.push_back(copies);
+        cigar_chars.insert(cigar_chars.end(), cigar_text, cigar_text + cigar_len);
+        seq_chars.insert(seq_chars.end(), letters, letters + n_letters);
+        cigar_off.push_back((int64_t)cigar_chars.size());
+        seq_off.push_back((int64_t)seq_chars.size());
+    }
 };
 
 // The graph as arrays.  Node ids are the reference's ids (index into its `nodes` vector).
@@ -44,10 +60,10 @@ struct FlatGraph
     std::vector<int> in_off;           // ordered predecessors (dump / parity only)
     std::vector<int> in_from;
     std::vector<int> pool_off;         // n_nodes+1, CSR of ordered read-pool entries
-    std::vector<int> pool_rid;
-    std::vector<int> pool_cn;
-    std::vector<int> pool_str_off;     // entries+1, into pool_chars
-    std::vector<char> pool_chars;
+    HostVec<int> pool_rid;             // (the four per-entry arrays come from the host block cache, common.hpp)
+    HostVec<int> pool_cn;
+    HostVec<int> pool_str_off;         // entries+1, into pool_chars
+    HostVec<char> pool_chars;
     int end_node = -1;                 // id of "$"
 
     std::string label(int u) const { return std::string(label_chars.data() + label_off[u], label_chars.data() + label_off[u + 1]); }
@@ -69,7 +85,7 @@ public:
     GraphBuilder& operator=(const GraphBuilder&) = delete;
 
     // phase A; appends this graph's alignment problems to `batch` and remembers where they start
-    void thread(const std::string& gene, const std::vector<AlignedRead>& reads, MsaBatch& batch);
+    void thread(const std::string& gene, const ReadSet& reads, MsaBatch& batch);
     // phase C; `rows` holds the solved problems of the batch that thread() appended to
     void finish(const MsaResult& rows, FlatGraph& out);
     int n_problems() const;
