@@ -996,12 +996,16 @@ struct Engine
     int run_walk(int forced_nb, int forced_tile, int forced_cluster)
     {
         const size_t n = subs.size();
+        const auto w0 = std::chrono::steady_clock::now();
+        auto lap = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count(); };
+        double ms_plan = 0, ms_fill = 0, ms_launch = 0, ms_kernel_done = 0;
         plans.assign(n, WalkPlan());
         auto each = [&](const std::function<void(size_t)>& fn) {
             if (workers) workers->run(n, fn);
             else for (size_t i = 0; i < n; ++i) fn(i);
         };
         each([&](size_t i) { plan_walk(i); });
+        ms_plan = lap();
         for (const WalkPlan& p : plans) stats.offtable_levels += p.mixed_levels;
         std::vector<int> take;
         size_t stat_bytes = 0, scr_bytes = 0;
@@ -1152,6 +1156,7 @@ struct Engine
         };
         if (workers && take.size() >= 4) workers->run(take.size(), fill);
         else for (size_t k = 0; k < take.size(); ++k) fill(k);
+        ms_fill = lap();
         RAMBL_CUDA(cudaMemcpyAsync(d_static.p, H, stat_bytes, cudaMemcpyHostToDevice, st));
         stats.h2d_bytes += (long long)stat_bytes;
         // ---- descriptors
@@ -1247,6 +1252,7 @@ struct Engine
         RAMBL_CUDA(cudaEventRecord(e0, st));
         launch_walk(d_walk.p, (int)take.size(), wp, nb, tile, cluster, st, &stats.launches);
         RAMBL_CUDA(cudaEventRecord(e1, st));
+        ms_launch = lap();
         // ---- results
         std::vector<WalkResult> res(take.size());
         std::vector<int> all_slot(take.size() * WALK_SMAX);
@@ -1255,6 +1261,7 @@ struct Engine
         RAMBL_CUDA(cudaMemcpyAsync(all_slot.data(), d_final_slot.p, sizeof(int) * all_slot.size(), cudaMemcpyDeviceToHost, st));
         RAMBL_CUDA(cudaMemcpyAsync(all_ab.data(), d_final_ab.p, sizeof(double) * all_ab.size(), cudaMemcpyDeviceToHost, st));
         RAMBL_CUDA(cudaStreamSynchronize(st));
+        ms_kernel_done = lap();
         stats.d2h_bytes += (long long)(sizeof(WalkResult) * res.size() + 12 * all_slot.size());
         float ms = 0;
         RAMBL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
@@ -1363,6 +1370,9 @@ struct Engine
         }
         if (!redo.empty() && getenv("RAMBL_TRACE"))
             fprintf(stderr, "[rambl] device walk: %zu subgroups handed back to the level-synchronous path\n", redo.size());
+        if (getenv("RAMBL_TRACE"))
+            fprintf(stderr, "[rambl] device walk host ms: plans until %.1f, tables filled %.1f, launched %.1f, kernel and results back %.1f, closed %.1f\n",
+                    ms_plan, ms_fill, ms_launch, ms_kernel_done, lap());
         return taken;
     }
 };
@@ -1463,6 +1473,7 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
     std::vector<std::vector<double>> infer_ab(E.subs.size());
     for (size_t i = 0; i < E.subs.size(); ++i)
         for (const Cand& c : E.subs[i].result) infer_ab[i].push_back(c.ab);
+    const double ms_before_assign = since(w0);
     if (prm.assign)
     {
         const double* al = E.assign_step();
@@ -1526,8 +1537,8 @@ void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, s
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (getenv("RAMBL_TRACE"))
-        fprintf(stderr, "[rambl] infer wall ms: start %.1f, walk+assign until %.1f, kernel times until %.1f, gather until %.1f\n",
-                ms_start, ms_walk, ms_times, since(w0));
+        fprintf(stderr, "[rambl] infer wall ms: start %.1f, walk until %.1f, read_assign until %.1f, kernel times until %.1f, gather until %.1f\n",
+                ms_start, ms_before_assign, ms_walk, ms_times, since(w0));
 }
 
 }  // namespace rambl
