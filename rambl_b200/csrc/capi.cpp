@@ -587,9 +587,13 @@ int rambl_batch_infer(rambl_batch* b, int32_t n, float e, float tau, float diff,
     });
 }
 
-// rambl_batch_build_graphs + rambl_batch_infer as ONE call that overlaps them: the subgroups are dealt into chunks,
-// two driver threads (each with its own CUDA stream) take chunks in order, so the host builds the graphs of one chunk
-// while the device walks the previous one.  Results are what the two separate calls give (subgroups never interact).
+// rambl_batch_build_graphs + rambl_batch_infer as ONE call that overlaps them.  The subgroups are dealt into chunks --
+// the first is one wave of the walk kernel (one subgroup per SM), so that the device starts as early as possible; the rest
+// follows in one chunk (several for very large batches) -- and two driver threads, each with its own CUDA stream, take the
+// chunks in order.  The host-heavy part of a chunk (graph construction and the level tables, on all worker threads) is
+// done by one driver at a time; it ends when the chunk's walk kernel is in its stream, and the other driver starts on the
+// next chunk while that kernel runs.  Kernels of consecutive chunks share the SMs: the later one fills in as the CTAs of
+// the earlier one retire.  Results are what the two separate calls give (subgroups never interact).
 int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff, int32_t do_assign, int32_t keep_loglik)
 {
     return guarded([&] {
@@ -598,14 +602,35 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
         const size_t N = b->subs.size();
         bool fresh = b->threaded_upto == 0 && b->msa.problems() == 0;
         for (auto& sp : b->subs) fresh = fresh && !sp->built;
-        // small batches gain nothing from chunks (their chains are latency-bound and get clusters instead)
-        size_t n_chunks = N >= 192 ? 4 : (N >= 96 ? 2 : 1);
+        int device = 0, sms = 148;
+        RAMBL_CUDA(cudaGetDevice(&device));
+        RAMBL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        // chunk bounds.  A batch of up to one wave gains nothing from chunks (its chains are latency-bound and get
+        // clusters instead).  $RAMBL_SOLVE_CHUNKS = k: k equal chunks; $RAMBL_SOLVE_FIRST = n: size of the first chunk.
+        std::vector<size_t> bound(1, 0);
         size_t n_drivers = 2;
-        if (const char* ev = getenv("RAMBL_SOLVE_CHUNKS")) n_chunks = std::max(1, atoi(ev));
-        if (const char* ev = getenv("RAMBL_SOLVE_DRIVERS")) n_drivers = std::max(1, atoi(ev));
-        n_chunks = std::min(n_chunks, std::max<size_t>(N, 1));
-        n_drivers = std::min(n_drivers, n_chunks);
-        if (!fresh || n_chunks == 1)
+        {
+            size_t first = (size_t)std::max(sms, 1);
+            if (const char* ev = getenv("RAMBL_SOLVE_FIRST")) first = (size_t)std::max(1, atoi(ev));
+            const char* ev = getenv("RAMBL_SOLVE_CHUNKS");
+            if (ev && atoi(ev) >= 1)
+            {
+                const size_t k = std::min<size_t>((size_t)atoi(ev), std::max<size_t>(N, 1));
+                for (size_t c = 1; c <= k; ++c) bound.push_back(N * c / k);
+            }
+            else if (N <= first) bound.push_back(N);
+            else
+            {
+                bound.push_back(first);
+                const size_t rest = N - first, cap = 8 * (size_t)std::max(sms, 1);
+                const size_t k = (rest + cap - 1) / cap;
+                for (size_t c = 1; c <= k; ++c) bound.push_back(first + rest * c / k);
+            }
+            if (const char* ev2 = getenv("RAMBL_SOLVE_DRIVERS")) n_drivers = (size_t)std::max(1, atoi(ev2));
+        }
+        const size_t n_chunks = bound.size() - 1;
+        n_drivers = std::min(n_drivers, std::max<size_t>(n_chunks, 1));
+        if (!fresh || n_chunks <= 1)
         {   // nothing to overlap (or a batch that is partly built already): the two calls, one after the other
             int rc = rambl_batch_build_graphs(b);
             if (rc != RAMBL_OK) throw Error(rc, g_error);
@@ -616,10 +641,8 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
         InferParams prm;
         prm.n = n; prm.e = e; prm.tau = tau; prm.diff = diff; prm.assign = do_assign != 0; prm.keep_loglik = keep_loglik != 0;
         prm.max_cluster = 1;  // the kernels of consecutive chunks share the SMs: one CTA per subgroup
-        int device = 0;
-        RAMBL_CUDA(cudaGetDevice(&device));
-        std::atomic<size_t> next(0);
-        std::mutex mu, build_mu;
+        size_t next = 0;      // guarded by host_mu
+        std::mutex mu, host_mu;
         std::string what;
         int code = RAMBL_OK;
         const auto w0 = std::chrono::steady_clock::now();
@@ -631,16 +654,16 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
                 RAMBL_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
                 for (;;)
                 {
-                    const size_t c = next.fetch_add(1);
+                    // ---- the host-heavy phase of one chunk at a time, chunks in order
+                    std::unique_lock<std::mutex> host_phase(host_mu);
+                    const size_t c = next;
                     {
                         std::lock_guard<std::mutex> lk(mu);
                         if (c >= n_chunks || code != RAMBL_OK) break;
                     }
-                    const size_t lo = N * c / n_chunks, hi = N * (c + 1) / n_chunks;
-                    // ---- graphs of this chunk: splice, align the insertion levels on the device, finish.  One chunk is
-                    // built at a time, on all host threads -- the other driver is in its device phase meanwhile; two
-                    // builds at once would only share the cores and leave the device idle until both are done.
-                    std::unique_lock<std::mutex> build_lock(build_mu);
+                    next += 1;
+                    const size_t lo = bound[c], hi = bound[c + 1];
+                    // graphs of this chunk: splice, align the insertion levels on the device, finish
                     std::vector<MsaBatch> local(hi - lo);
                     parallel_for(lo, hi, [&](size_t i) {
                         Subgroup& s = *b->subs[i];
@@ -668,13 +691,15 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
                         s.input.graph = &s.graph;
                         s.built = true;
                     });
-                    build_lock.unlock();
-                    // ---- strain search of this chunk
+                    // ---- strain search of this chunk; the host phase is over once its walk kernel is launched
                     std::vector<SubgroupInput> in;
                     for (size_t i = lo; i < hi; ++i) in.push_back(b->subs[i]->input);
                     std::vector<SubgroupResult> out;
                     EngineStats es;
-                    infer_batch(in, prm, out, es, st);
+                    InferParams mine = prm;
+                    mine.on_device_phase = [&host_phase] { if (host_phase.owns_lock()) host_phase.unlock(); };
+                    infer_batch(in, mine, out, es, st);
+                    if (host_phase.owns_lock()) host_phase.unlock();
                     std::lock_guard<std::mutex> lk(mu);
                     for (size_t i = lo; i < hi; ++i) { b->subs[i]->result = std::move(out[i - lo]); b->subs[i]->inferred = true; }
                     b->stats.gpu_launches += rows.launches + es.launches;

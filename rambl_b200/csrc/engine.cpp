@@ -1091,6 +1091,7 @@ struct Engine
                     RAMBL_CUDA(cudaSetDevice(device));
                     InferParams p2 = prm;
                     p2.level_synchronous = true;
+                    p2.on_device_phase = nullptr;
                     infer_batch(side_in, p2, side_out, side_stats, side_stream);
                 }
                 catch (...) { side_error = std::current_exception(); }
@@ -1253,6 +1254,7 @@ struct Engine
         launch_walk(d_walk.p, (int)take.size(), wp, nb, tile, cluster, st, &stats.launches);
         RAMBL_CUDA(cudaEventRecord(e1, st));
         ms_launch = lap();
+        if (prm.on_device_phase) prm.on_device_phase();
         // ---- results
         std::vector<WalkResult> res(take.size());
         std::vector<int> all_slot(take.size() * WALK_SMAX);

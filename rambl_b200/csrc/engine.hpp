@@ -9,6 +9,7 @@
 // level -- while everything that is per read x strain runs on the device, level-synchronously over
 // all subgroups: one set of launches per graph level regardless of how many subgroups there are.
 #pragma once
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -26,6 +27,9 @@ struct InferParams
     bool keep_loglik = false;  // also return the per-read log-likelihood rows of the inferred strains
     int max_cluster = 0;  // > 0: at most this many CTAs per subgroup in the walk (the overlapped solve runs several chunks' kernels side by side)
     bool level_synchronous = false;  // this call: the level-synchronous path only (the side batch of subgroups the walk cannot take)
+    // called on the calling thread once the walk kernel is in its stream, i.e. when the host-heavy set-up of the call is
+    // over (not called when nothing goes to the walk): the overlapped solve starts the next chunk's host work then
+    std::function<void()> on_device_phase;
 };
 
 struct StrainResult

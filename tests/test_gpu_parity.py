@@ -399,11 +399,16 @@ def test_full_size_properties(cfg):
         assert np.all(np.isfinite(s.read_loglik)) and np.all(s.read_loglik <= 0)
 
 
-def test_overlapped_solve_equals_build_then_infer():
+@pytest.mark.parametrize("layout", [{}, {"RAMBL_SOLVE_FIRST": "7"}, {"RAMBL_SOLVE_CHUNKS": "3"},
+                                    {"RAMBL_SOLVE_CHUNKS": "5", "RAMBL_SOLVE_DRIVERS": "3"}])
+def test_overlapped_solve_equals_build_then_infer(layout, monkeypatch):
     """rambl_batch_solve (chunks on two streams, graph construction of one chunk under the strain search of the previous)
-    gives, subgroup by subgroup, the text of rambl_batch_build_graphs + rambl_batch_infer."""
+    gives, subgroup by subgroup, the text of rambl_batch_build_graphs + rambl_batch_infer -- for the default layout (a
+    batch of up to one wave is one chunk) and for layouts that force several chunks on this small batch."""
     sgs = [synth.make_subgroup(**fuzz_spec(s)) for s in range(24)]
     a = _solve(sgs)
+    for k, v in layout.items():
+        monkeypatch.setenv(k, v)
     b = api.StrainCallBatch()
     for sg in sgs:
         b.add(sg)
