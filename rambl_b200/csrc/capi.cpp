@@ -641,11 +641,30 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
         InferParams prm;
         prm.n = n; prm.e = e; prm.tau = tau; prm.diff = diff; prm.assign = do_assign != 0; prm.keep_loglik = keep_loglik != 0;
         prm.max_cluster = 1;  // the kernels of consecutive chunks share the SMs: one CTA per subgroup
+        // ---- every subgroup's reads are spliced and ALL insertion levels are aligned first, in one launch set, while the
+        // device is idle: an alignment launch of a later chunk would wait for a free SM behind the walk kernel of the
+        // chunk before it (a walk CTA takes the whole shared memory of its SM for ~0.5 s or more)
+        const auto w0 = std::chrono::steady_clock::now();
+        MsaResult rows;
+        {
+            thread_pending(b);
+            cudaStream_t st0 = nullptr;
+            RAMBL_CUDA(cudaStreamCreateWithFlags(&st0, cudaStreamNonBlocking));
+            try { msa_sp_align_batch(b->msa, rows, st0); }
+            catch (...) { cudaStreamDestroy(st0); throw; }
+            cudaStreamDestroy(st0);
+            b->stats.gpu_launches += rows.launches;
+            b->stats.msa_dp_cells += (int64_t)rows.dp_cells;
+            b->stats.msa_problems += b->msa.problems();
+            b->stats.msa_kernel_ms += rows.kernel_ms;
+            b->stats.h2d_bytes += (int64_t)(b->msa.chars.size() + 4 * (b->msa.seq_off.size() + b->msa.prob_seq_off.size()));
+            b->stats.d2h_bytes += (int64_t)rows.rows.size();
+        }
+        const double ms_threaded = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
         size_t next = 0;      // guarded by host_mu
         std::mutex mu, host_mu;
         std::string what;
         int code = RAMBL_OK;
-        const auto w0 = std::chrono::steady_clock::now();
         auto drive = [&] {
             cudaStream_t st = nullptr;
             try
@@ -663,27 +682,7 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
                     }
                     next += 1;
                     const size_t lo = bound[c], hi = bound[c + 1];
-                    // graphs of this chunk: splice, align the insertion levels on the device, finish
-                    std::vector<MsaBatch> local(hi - lo);
-                    parallel_for(lo, hi, [&](size_t i) {
-                        Subgroup& s = *b->subs[i];
-                        s.builder.reset(new GraphBuilder);
-                        s.builder->thread(s.gene, s.reads, local[i - lo]);
-                    });
-                    MsaBatch msa;
-                    for (size_t i = lo; i < hi; ++i)
-                    {
-                        const MsaBatch& m = local[i - lo];
-                        b->subs[i]->builder->rebase_problems(msa.problems());
-                        for (int p = 0; p < m.problems(); ++p)
-                        {
-                            for (int q = m.prob_seq_off[p]; q < m.prob_seq_off[p + 1]; ++q)
-                                msa.add_sequence(m.chars.data() + m.seq_off[q], m.seq_off[q + 1] - m.seq_off[q]);
-                            msa.end_problem();
-                        }
-                    }
-                    MsaResult rows;
-                    msa_sp_align_batch(msa, rows, st);
+                    // graphs of this chunk: canonise with the aligned rows, merge, collapse, level, flatten
                     parallel_for(lo, hi, [&](size_t i) {
                         Subgroup& s = *b->subs[i];
                         s.builder->finish(rows, s.graph);
@@ -702,12 +701,9 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
                     if (host_phase.owns_lock()) host_phase.unlock();
                     std::lock_guard<std::mutex> lk(mu);
                     for (size_t i = lo; i < hi; ++i) { b->subs[i]->result = std::move(out[i - lo]); b->subs[i]->inferred = true; }
-                    b->stats.gpu_launches += rows.launches + es.launches;
-                    b->stats.msa_dp_cells += (int64_t)rows.dp_cells;
-                    b->stats.msa_problems += msa.problems();
-                    b->stats.msa_kernel_ms += rows.kernel_ms;
-                    b->stats.h2d_bytes += (int64_t)(msa.chars.size() + 4 * (msa.seq_off.size() + msa.prob_seq_off.size())) + es.h2d_bytes;
-                    b->stats.d2h_bytes += (int64_t)rows.rows.size() + es.d2h_bytes;
+                    b->stats.gpu_launches += es.launches;
+                    b->stats.h2d_bytes += es.h2d_bytes;
+                    b->stats.d2h_bytes += es.d2h_bytes;
                     b->stats.level_steps += es.level_steps;
                     b->stats.draws += es.draws;
                     b->stats.loglik_updates += es.loglik_updates;
@@ -743,8 +739,8 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
         b->msa = MsaBatch();
         b->last = prm;
         if (getenv("RAMBL_TRACE"))
-            fprintf(stderr, "[rambl] rambl_batch_solve: %zu subgroups in %zu chunks, %.1f ms\n", N, n_chunks,
-                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count());
+            fprintf(stderr, "[rambl] rambl_batch_solve: %zu subgroups in %zu chunks, reads spliced and insertions aligned after %.1f ms, %.1f ms in all\n",
+                    N, n_chunks, ms_threaded, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count());
         if (code != RAMBL_OK) throw Error(code, what);
     });
 }

@@ -1304,21 +1304,30 @@ struct Engine
         }
         int taken = 0;
         std::vector<size_t> redo;
+        std::vector<char> solved(take.size(), 0);
         for (size_t k = 0; k < take.size(); ++k)
         {
             const WalkResult& r = res[k];
-            Sub& s = subs[take[k]];
             if (r.status >= WALK_TOO_MANY_STRAINS) { redo.push_back(take[k]); continue; }
             stats.draws += r.draws;
             stats.loglik_updates += r.loglik_updates;
             stats.walk_bytes += r.gibbs_bytes + 16 * r.loglik_updates + 16 * r.weight_pairs;
             stats.gibbs_bytes += r.gibbs_bytes;
+            solved[k] = 1;
+        }
+        // the candidates and their paths, and "$" (sort + merge_strains: the strains keep their slots, the walk is over):
+        // per subgroup, nothing shared -- on the workers
+        auto close_one = [&](size_t k) {
+            if (!solved[k]) return;
+            const WalkResult& r = res[k];
+            Sub& s = subs[take[k]];
             s.draws += r.draws;
             s.levels = plans[take[k]].n_levels;
             s.done = true;
             s.cands.clear();
             s.trail.clear();
             const int nl = plans[take[k]].n_levels;
+            s.trail.reserve((size_t)std::max(r.n_cands, 0) * (size_t)nl);
             for (int c = 0; c < r.n_cands; ++c)
             {
                 Cand cd;
@@ -1330,12 +1339,17 @@ struct Engine
                 cd.node = s.g->end_node;
                 s.cands.push_back(cd);
             }
-            if (!plans[take[k]].handoff)
-            {
-                close_result(s, false);  // "$": sort + merge_strains; the walk is over, the strains keep their slots
-                ++taken;
-                continue;
-            }
+            if (!plans[take[k]].handoff) close_result(s, false);
+        };
+        if (workers && take.size() >= 4) workers->run(take.size(), close_one);
+        else for (size_t k = 0; k < take.size(); ++k) close_one(k);
+        for (size_t k = 0; k < take.size(); ++k)
+        {
+            if (!solved[k]) continue;
+            if (!plans[take[k]].handoff) { ++taken; continue; }
+            const WalkResult& r = res[k];
+            Sub& s = subs[take[k]];
+            const int nl = plans[take[k]].n_levels;
             // the walk stopped in front of a level that holds "$" next to other nodes: the level-synchronous path takes the
             // subgroup over exactly there (candidates, presence flags, free slots, the level's nodes)
             {
