@@ -118,34 +118,46 @@ void parallel_for(size_t lo, size_t hi, F&& fn)
     if (failed.load()) throw Error(code, what);
 }
 
-// phase A for the subgroups added since the last call; every subgroup lists its alignment problems
-// privately, the lists are then appended to the batch in subgroup order
-void thread_pending(rambl_batch* b)
+// phase A for subgroups [lo, hi): every subgroup lists its alignment problems privately, the lists are then appended to
+// `into` in subgroup order.  A subgroup without alignment problems (the common case when the strains differ by
+// substitutions) needs nothing from the device: it is finished at once, on the same worker -- its builder's memory is
+// still in cache and goes back to the allocator for the next subgroup, instead of 5 MB per subgroup lying cold until a
+// second pass.
+void thread_range(rambl_batch* b, size_t lo, size_t hi, MsaBatch& into)
 {
-    const size_t lo = b->threaded_upto, hi = b->subs.size();
     std::vector<MsaBatch> local(hi - lo);
+    static const MsaResult no_rows;
     parallel_for(lo, hi, [&](size_t i) {
         Subgroup& s = *b->subs[i];
+        if (s.built) return;
         s.builder.reset(new GraphBuilder);
         s.builder->thread(s.gene, s.reads, local[i - lo]);
+        if (s.builder->n_problems() == 0)
+        {
+            s.builder->finish(no_rows, s.graph);
+            s.builder.reset();
+            s.input.graph = &s.graph;
+            s.built = true;
+        }
     });
     for (size_t i = lo; i < hi; ++i)
     {
         const MsaBatch& m = local[i - lo];
-        b->subs[i]->builder->rebase_problems(b->msa.problems());
+        if (!b->subs[i]->builder) continue;
+        b->subs[i]->builder->rebase_problems(into.problems());
         for (int p = 0; p < m.problems(); ++p)
         {
             for (int q = m.prob_seq_off[p]; q < m.prob_seq_off[p + 1]; ++q)
-                b->msa.add_sequence(m.chars.data() + m.seq_off[q], m.seq_off[q + 1] - m.seq_off[q]);
-            b->msa.end_problem();
+                into.add_sequence(m.chars.data() + m.seq_off[q], m.seq_off[q + 1] - m.seq_off[q]);
+            into.end_problem();
         }
     }
-    b->threaded_upto = hi;
 }
 
-void finish_pending(rambl_batch* b, const MsaResult& rows)
+// phase C for the subgroups of [lo, hi) that wait for aligned rows
+void finish_range(rambl_batch* b, size_t lo, size_t hi, const MsaResult& rows)
 {
-    parallel_for(0, b->subs.size(), [&](size_t i) {
+    parallel_for(lo, hi, [&](size_t i) {
         Subgroup& s = *b->subs[i];
         if (s.built || !s.builder) return;
         s.builder->finish(rows, s.graph);
@@ -153,6 +165,18 @@ void finish_pending(rambl_batch* b, const MsaResult& rows)
         s.input.graph = &s.graph;
         s.built = true;
     });
+}
+
+// phase A for the subgroups added since the last call
+void thread_pending(rambl_batch* b)
+{
+    thread_range(b, b->threaded_upto, b->subs.size(), b->msa);
+    b->threaded_upto = b->subs.size();
+}
+
+void finish_pending(rambl_batch* b, const MsaResult& rows)
+{
+    finish_range(b, 0, b->subs.size(), rows);
     b->msa = MsaBatch();
 }
 
@@ -610,7 +634,10 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
         std::vector<size_t> bound(1, 0);
         size_t n_drivers = 2;
         {
-            size_t first = (size_t)std::max(sms, 1);
+            // one wave minus a few SMs: a walk CTA takes the whole shared memory of its SM for half a second or more, and
+            // the small launches of the NEXT chunk's set-up (its insertion alignment, the model initialisation) need
+            // somewhere to run before the first walk CTAs retire
+            size_t first = (size_t)std::max(sms - 8, 1);
             if (const char* ev = getenv("RAMBL_SOLVE_FIRST")) first = (size_t)std::max(1, atoi(ev));
             const char* ev = getenv("RAMBL_SOLVE_CHUNKS");
             if (ev && atoi(ev) >= 1)
@@ -641,26 +668,7 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
         InferParams prm;
         prm.n = n; prm.e = e; prm.tau = tau; prm.diff = diff; prm.assign = do_assign != 0; prm.keep_loglik = keep_loglik != 0;
         prm.max_cluster = 1;  // the kernels of consecutive chunks share the SMs: one CTA per subgroup
-        // ---- every subgroup's reads are spliced and ALL insertion levels are aligned first, in one launch set, while the
-        // device is idle: an alignment launch of a later chunk would wait for a free SM behind the walk kernel of the
-        // chunk before it (a walk CTA takes the whole shared memory of its SM for ~0.5 s or more)
         const auto w0 = std::chrono::steady_clock::now();
-        MsaResult rows;
-        {
-            thread_pending(b);
-            cudaStream_t st0 = nullptr;
-            RAMBL_CUDA(cudaStreamCreateWithFlags(&st0, cudaStreamNonBlocking));
-            try { msa_sp_align_batch(b->msa, rows, st0); }
-            catch (...) { cudaStreamDestroy(st0); throw; }
-            cudaStreamDestroy(st0);
-            b->stats.gpu_launches += rows.launches;
-            b->stats.msa_dp_cells += (int64_t)rows.dp_cells;
-            b->stats.msa_problems += b->msa.problems();
-            b->stats.msa_kernel_ms += rows.kernel_ms;
-            b->stats.h2d_bytes += (int64_t)(b->msa.chars.size() + 4 * (b->msa.seq_off.size() + b->msa.prob_seq_off.size()));
-            b->stats.d2h_bytes += (int64_t)rows.rows.size();
-        }
-        const double ms_threaded = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
         size_t next = 0;      // guarded by host_mu
         std::mutex mu, host_mu;
         std::string what;
@@ -682,14 +690,16 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
                     }
                     next += 1;
                     const size_t lo = bound[c], hi = bound[c + 1];
-                    // graphs of this chunk: canonise with the aligned rows, merge, collapse, level, flatten
-                    parallel_for(lo, hi, [&](size_t i) {
-                        Subgroup& s = *b->subs[i];
-                        s.builder->finish(rows, s.graph);
-                        s.builder.reset();
-                        s.input.graph = &s.graph;
-                        s.built = true;
-                    });
+                    // graphs of this chunk: splice (and finish what needs no alignment), align the insertion levels of the
+                    // others on the device, finish those
+                    MsaBatch msa;
+                    MsaResult rows;
+                    thread_range(b, lo, hi, msa);
+                    if (msa.problems() > 0)
+                    {
+                        msa_sp_align_batch(msa, rows, st);
+                        finish_range(b, lo, hi, rows);
+                    }
                     // ---- strain search of this chunk; the host phase is over once its walk kernel is launched
                     std::vector<SubgroupInput> in;
                     for (size_t i = lo; i < hi; ++i) in.push_back(b->subs[i]->input);
@@ -701,9 +711,12 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
                     if (host_phase.owns_lock()) host_phase.unlock();
                     std::lock_guard<std::mutex> lk(mu);
                     for (size_t i = lo; i < hi; ++i) { b->subs[i]->result = std::move(out[i - lo]); b->subs[i]->inferred = true; }
-                    b->stats.gpu_launches += es.launches;
-                    b->stats.h2d_bytes += es.h2d_bytes;
-                    b->stats.d2h_bytes += es.d2h_bytes;
+                    b->stats.gpu_launches += rows.launches + es.launches;
+                    b->stats.msa_dp_cells += (int64_t)rows.dp_cells;
+                    b->stats.msa_problems += msa.problems();
+                    b->stats.msa_kernel_ms += rows.kernel_ms;
+                    b->stats.h2d_bytes += (int64_t)(msa.chars.size() + 4 * (msa.seq_off.size() + msa.prob_seq_off.size())) + es.h2d_bytes;
+                    b->stats.d2h_bytes += (int64_t)rows.rows.size() + es.d2h_bytes;
                     b->stats.level_steps += es.level_steps;
                     b->stats.draws += es.draws;
                     b->stats.loglik_updates += es.loglik_updates;
@@ -739,8 +752,8 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
         b->msa = MsaBatch();
         b->last = prm;
         if (getenv("RAMBL_TRACE"))
-            fprintf(stderr, "[rambl] rambl_batch_solve: %zu subgroups in %zu chunks, reads spliced and insertions aligned after %.1f ms, %.1f ms in all\n",
-                    N, n_chunks, ms_threaded, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count());
+            fprintf(stderr, "[rambl] rambl_batch_solve: %zu subgroups in %zu chunks, %.1f ms\n", N, n_chunks,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count());
         if (code != RAMBL_OK) throw Error(code, what);
     });
 }
