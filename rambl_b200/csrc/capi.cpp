@@ -645,7 +645,7 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
                 const size_t k = std::min<size_t>((size_t)atoi(ev), std::max<size_t>(N, 1));
                 for (size_t c = 1; c <= k; ++c) bound.push_back(N * c / k);
             }
-            else if (N <= first) bound.push_back(N);
+            else if (N <= first || (!getenv("RAMBL_SOLVE_FIRST") && N <= (size_t)std::max(sms, 1))) bound.push_back(N);
             else
             {
                 bound.push_back(first);

@@ -1255,7 +1255,11 @@ struct Engine
         RAMBL_CUDA(cudaEventRecord(e1, st));
         ms_launch = lap();
         if (prm.on_device_phase) prm.on_device_phase();
-        // ---- results
+        // ---- results.  Wait for the kernel FIRST: an asynchronous copy into pageable host memory queued behind a running
+        // kernel keeps the calling thread inside the driver until the kernel ends, and (measured) the CUDA calls of
+        // every other thread of the process wait with it -- the next chunk of an overlapped solve could not set up its
+        // own walk while this one ran.  cudaStreamSynchronize holds nothing.
+        RAMBL_CUDA(cudaStreamSynchronize(st));
         std::vector<WalkResult> res(take.size());
         std::vector<int> all_slot(take.size() * WALK_SMAX);
         std::vector<double> all_ab(take.size() * WALK_SMAX);
