@@ -150,8 +150,9 @@ int rambl_batch_finish_graphs_with_rows(rambl_batch* b, const char* rows_text);
  * degenerate abundances) get RAMBL_ERR_CAPACITY; the call itself still returns RAMBL_OK. */
 int rambl_batch_infer(rambl_batch* b, int32_t n, float e, float tau, float diff, int32_t do_assign, int32_t keep_loglik);
 
-/* rambl_batch_build_graphs + rambl_batch_infer in one call that overlaps them: the batch is dealt into chunks and the
- * host builds the graphs of one chunk while the device searches the strains of the previous one (two CUDA streams).
+/* rambl_batch_build_graphs + rambl_batch_infer in one call that overlaps them: a batch of more than one wave of the walk
+ * kernel (one subgroup per SM) is dealt into a first chunk of one wave and the rest, and the host builds the graphs of the
+ * second chunk while the device searches the strains of the first (two CUDA streams, two driver threads).
  * Same results as the two calls (subgroups never interact); what StrainCall's main() loop is to the CLI. */
 int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff, int32_t do_assign, int32_t keep_loglik);
 
