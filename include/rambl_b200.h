@@ -63,8 +63,12 @@ int rambl_device_count(void);
 int rambl_set_device(int32_t device);
 void rambl_free(void* p); /* for every char* this library returns */
 /* Device and pinned-host buffers are cached between calls (cudaMalloc/cudaFree cost up to a second per
- * strain search); this returns the cached blocks to the driver. */
+ * strain search), and so are the large pageable host arrays of the flat graphs (fresh pages were a fifth of graph
+ * construction; at most $RAMBL_HOST_CACHE_MB, default 16384, the blocks released longest ago go first); this returns all
+ * cached blocks to the driver / the allocator. */
 void rambl_release_cached_memory(void);
+/* Bytes of pageable host memory the cache holds right now (released by batches, not yet reused). */
+int64_t rambl_cached_host_bytes(void);
 /* The Gibbs-sweep kernels take 1, 2, 4 or 8 blocks of 32 draws per round; 0 (the default) lets the library
  * choose by batch size and strain count.  -1, -2, -4 pin the block count AND the four-warps-per-block kernel
  * that otherwise serves only levels of more than 64 strains.  Every setting computes the same chain -- this

@@ -57,6 +57,7 @@ SYMBOLS = {
     "rambl_set_device": (C.c_int, [C.c_int32]),
     "rambl_free": (None, [C.c_void_p]),
     "rambl_release_cached_memory": (None, []),
+    "rambl_cached_host_bytes": (C.c_int64, []),
     "rambl_set_gibbs_blocks": (C.c_int, [C.c_int32]),
     "rambl_set_host_threads": (C.c_int, [C.c_int32]),
     "rambl_set_walk_mode": (C.c_int, [C.c_int32]),
@@ -137,6 +138,16 @@ def _i32(a) -> np.ndarray:
 
 def device_count() -> int:
     return lib().rambl_device_count()
+
+
+def release_cached_memory() -> None:
+    """Cached device, pinned and pageable host blocks go back to the driver / the allocator."""
+    lib().rambl_release_cached_memory()
+
+
+def cached_host_bytes() -> int:
+    """Pageable host memory the library's block cache holds right now."""
+    return int(lib().rambl_cached_host_bytes())
 
 
 # ------------------------------------------------------------------------------------------------

@@ -244,6 +244,7 @@ int rambl_set_device(int32_t device)
 void rambl_free(void* p) { free(p); }
 
 void rambl_release_cached_memory(void) { release_cached_memory(); }
+int64_t rambl_cached_host_bytes(void) { return (int64_t)cached_host_bytes(); }
 
 int rambl_set_gibbs_blocks(int32_t blocks)
 {

@@ -46,6 +46,7 @@ void release_cached_memory();
 // default 16 384; smaller requests are plain malloc).  release_cached_memory() frees them as well.
 void* cached_host_alloc(size_t bytes);
 void cached_host_free(void* p);
+size_t cached_host_bytes();  // held by the cache right now
 
 // std::vector allocator over the cache above; elements are default-initialised (resize() does not zero what the caller
 // is about to overwrite).

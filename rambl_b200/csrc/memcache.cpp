@@ -5,6 +5,7 @@
 #include <mutex>
 #include <new>
 #include <thread>
+#include <vector>
 
 #include "common.hpp"
 
@@ -102,13 +103,18 @@ void cached_pinned_free(void* p, size_t granted)
 }
 
 // ---- pageable host blocks (common.hpp: cached_host_alloc).  A block carries its capacity in a 64-byte header; a
-// request takes the smallest kept block that is large enough and at most half as large again.
+// request takes the smallest kept block that is large enough and at most half as large again.  When the kept blocks
+// would exceed the limit, the ones released longest ago go back to the allocator first (a workload whose subgroup sizes
+// change must not be left with a cache full of blocks that fit nothing).
 namespace {
 const size_t kHostHeader = 64, kHostSmall = 64 * 1024;
 struct HostCache
 {
+    struct Kept { void* base; unsigned long long stamp; };
     std::mutex mu;
-    std::multimap<size_t, void*> free_blocks;  // capacity -> block (header address)
+    std::multimap<size_t, Kept> by_size;                                            // capacity -> block
+    std::map<unsigned long long, std::multimap<size_t, Kept>::iterator> by_age;     // release order -> its entry
+    unsigned long long clock = 0;
     size_t held = 0, limit = 0;
 };
 HostCache& host_cache()
@@ -133,17 +139,19 @@ void* cached_host_alloc(size_t bytes)
         cap = (bytes + 0xffff) & ~(size_t)0xffff;
         HostCache& hc = host_cache();
         std::lock_guard<std::mutex> lk(hc.mu);
-        auto it = hc.free_blocks.lower_bound(cap);
-        if (it != hc.free_blocks.end() && it->first <= cap + cap / 2)
+        auto it = hc.by_size.lower_bound(cap);
+        if (it != hc.by_size.end() && it->first <= cap + cap / 2)
         {
-            base = it->second;
+            base = it->second.base;
             cap = it->first;
             hc.held -= cap;
-            hc.free_blocks.erase(it);
+            hc.by_age.erase(it->second.stamp);
+            hc.by_size.erase(it);
         }
     }
     if (!base)
     {
+        if (cap > (size_t)-1 - kHostHeader) throw std::bad_alloc();
         base = malloc(kHostHeader + cap);
         if (!base) throw std::bad_alloc();
     }
@@ -156,36 +164,57 @@ void cached_host_free(void* p)
     if (!p) return;
     void* base = static_cast<char*>(p) - kHostHeader;
     const size_t cap = *static_cast<size_t*>(base);
+    std::vector<void*> evicted;
+    bool kept = false;
     if (cap >= kHostSmall)
     {
         HostCache& hc = host_cache();
         std::lock_guard<std::mutex> lk(hc.mu);
-        if (hc.held + cap <= hc.limit)
+        if (cap <= hc.limit)
         {
-            hc.free_blocks.insert({cap, base});
+            while (hc.held + cap > hc.limit && !hc.by_age.empty())
+            {
+                auto oldest = hc.by_age.begin();
+                hc.held -= oldest->second->first;
+                evicted.push_back(oldest->second->second.base);
+                hc.by_size.erase(oldest->second);
+                hc.by_age.erase(oldest);
+            }
+            const unsigned long long stamp = ++hc.clock;
+            hc.by_age[stamp] = hc.by_size.insert({cap, HostCache::Kept{base, stamp}});
             hc.held += cap;
-            return;
+            kept = true;
         }
     }
-    free(base);
+    for (void* q : evicted) free(q);
+    if (!kept) free(base);
+}
+
+size_t cached_host_bytes()
+{
+    std::lock_guard<std::mutex> lk(host_cache().mu);
+    return host_cache().held;
 }
 
 void release_cached_memory()
 {
-    std::multimap<size_t, void*> d, h, m;
+    std::multimap<size_t, void*> d, h;
     {
         std::lock_guard<std::mutex> lk(cache().mu);
         d.swap(cache().device);
         h.swap(cache().pinned);
     }
+    std::vector<void*> blocks;
     {
         std::lock_guard<std::mutex> lk(host_cache().mu);
-        m.swap(host_cache().free_blocks);
+        for (auto& kv : host_cache().by_size) blocks.push_back(kv.second.base);
+        host_cache().by_size.clear();
+        host_cache().by_age.clear();
         host_cache().held = 0;
     }
     for (auto& kv : d) cudaFree(kv.second);
     for (auto& kv : h) cudaFreeHost(kv.second);
-    for (auto& kv : m) free(kv.second);
+    for (void* q : blocks) free(q);
 }
 
 }  // namespace rambl

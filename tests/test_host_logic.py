@@ -225,3 +225,75 @@ def test_random_cigars_match_oracle_or_are_refused():
         assert strip_sib(b.graph_dump(0)) == strip_sib(o.dump()), (gene, reads)
         assert b.output_edge(0) == o.edges()
     assert refused < 125
+
+
+def test_host_block_cache_keeps_and_reuses_the_flat_graph_arrays():
+    """The per-entry arrays of a flat graph (>= 64 KB each) go to the host block cache when the batch is closed, the next
+    batch takes them from there, and rambl_release_cached_memory() gives everything back."""
+    sg = synth.make_subgroup(n_reads=1500, read_len=100, n_strains=3, seed=5)
+    api.release_cached_memory()
+    assert api.cached_host_bytes() == 0
+    b, _ = _build_with_supplied_rows(sg)
+    dump = b.graph_dump(0)
+    assert api.cached_host_bytes() == 0  # in use, nothing released yet
+    b.close()
+    held = api.cached_host_bytes()
+    assert held >= 3 * 64 * 1024  # read ids, copies, string offsets (4 bytes per entry each) at least
+    b2, _ = _build_with_supplied_rows(sg)
+    assert api.cached_host_bytes() < held  # the same sizes again: taken from the cache
+    assert b2.graph_dump(0) == dump
+    b2.close()
+    assert api.cached_host_bytes() == held
+    api.release_cached_memory()
+    assert api.cached_host_bytes() == 0
+
+
+def test_host_block_cache_respects_its_limit():
+    """RAMBL_HOST_CACHE_MB bounds what is kept; the blocks released longest ago are dropped first."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from rambl_b200 import api, synth
+        from test_host_logic import _build_with_supplied_rows
+        held = []
+        for n in (1500, 3000, 1500):
+            b, _ = _build_with_supplied_rows(synth.make_subgroup(n_reads=n, read_len=100, n_strains=3, seed=5))
+            b.close()
+            held.append(api.cached_host_bytes())
+        print(held)
+        assert all(0 < h <= 1 << 20 for h in held), held
+    """) % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ, RAMBL_HOST_CACHE_MB="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_reads_as_strings_and_as_packed_arenas_give_the_same_graph():
+    """rambl_batch_add_subgroup (one C string per read), rambl_batch_add_subgroup_packed, and the packed call on arenas
+    whose first read does not start at offset 0 (a slice of a larger buffer) build identical graphs; offsets that
+    decrease are refused."""
+    import numpy as np
+    sg = synth.make_subgroup(**fuzz_spec(3))
+    pk = sg.packed()
+    dumps = []
+    for how in ("strings", "packed", "shifted"):
+        b = api.StrainCallBatch()
+        if how == "strings":
+            b.add_subgroup(sg.gene, sg.pos, sg.cigar, sg.seq, sg.cn, sg.pair_off, sg.pair_val)
+        elif how == "packed":
+            b.add(sg)
+        else:
+            b.add_subgroup_packed(sg.gene, pk["pos"], pk["cigar_off"] + 5, b"JUNK!" + pk["cigar_chars"], pk["seq_off"] + 3,
+                                  b"xyz" + pk["seq_chars"], pk["cn"], sg.pair_off, sg.pair_val)
+        b.thread_reads()
+        b.finish_graphs_with_rows([refpy.msa_align(p, "oracle") for p in b.msa_problems()])
+        dumps.append((b.graph_dump(0), b.output_edge(0)))
+        b.close()
+    assert dumps[0] == dumps[1] == dumps[2]
+    bad = api.StrainCallBatch()
+    off = np.array(pk["seq_off"], dtype=np.int64)
+    off[2] = off[1] - 1
+    with pytest.raises(api.RamblError):
+        bad.add_subgroup_packed(sg.gene, pk["pos"], pk["cigar_off"], pk["cigar_chars"], off, pk["seq_chars"], pk["cn"])
+    bad.close()
