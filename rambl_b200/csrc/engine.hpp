@@ -1,13 +1,15 @@
-// Strain inference over a batch of subgroups (host orchestration of the kernels in dpm.cu).
+// Strain inference over a batch of subgroups (host orchestration of the kernels in walk.cu and dpm.cu).
 //
 // Replaces, for every subgroup of the batch at once,
 //   PartialOrderGraph::infer_strains -> streaming_clustering  (NonparametricClustering.cpp:262-582,704-708)
 //   PartialOrderGraph::read_assign (AlignRead form)           (NonparametricClustering.cpp:776-836)
 //   the abundance sort of main()                              (StrainCall.cpp:1027)
-// The graph walk, the candidate bookkeeping (which strain extends over which edge, which strains
-// are dropped) and the final merge stay on the host -- they are a few hundred scalar decisions per
-// level -- while everything that is per read x strain runs on the device, level-synchronously over
-// all subgroups: one set of launches per graph level regardless of how many subgroups there are.
+// Two paths compute the same thing.  The device-resident walk (walk.cu, the default): the level structure of a graph is
+// turned into compact tables once, and ONE kernel walks every subgroup from "^" to "$" -- candidate bookkeeping included --
+// with one CTA or one thread-block cluster per subgroup; the host closes the results ("$": sort + merge_strains) and
+// launches read_assign.  The level-synchronous path (dpm.cu; what the walk cannot take, and the take-over after an early
+// "$"): the graph walk and the candidate bookkeeping stay on the host, everything per read x strain runs on the device,
+// one set of launches per graph level for all subgroups.
 #pragma once
 #include <functional>
 #include <string>
