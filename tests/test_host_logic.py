@@ -297,3 +297,23 @@ def test_reads_as_strings_and_as_packed_arenas_give_the_same_graph():
     with pytest.raises(api.RamblError):
         bad.add_subgroup_packed(sg.gene, pk["pos"], pk["cigar_off"], pk["cigar_chars"], off, pk["seq_chars"], pk["cn"])
     bad.close()
+
+
+def test_input_on_which_the_reference_never_ends_is_refused():
+    """Homopolymer indel errors can produce alignments whose canonised graph has a cycle; PartialOrderGraph::build (and the
+    oracle's restatement of it) then loops in path_collapse for ever -- checked with oracle/_ref under a 120 s timeout,
+    tools/ref_nonterminating.py.  The builder pays every loop into one work budget and refuses such a subgroup with
+    RAMBL_ERR_INVALID instead of hanging the batch."""
+    seed = 66
+    spec = dict(n_reads=300 + 7 * (seed % 50), read_len=60, n_strains=2 + seed % 4, seed=1000 + seed, window=(100, 400),
+                sub_err=0.005, indel_err=0.01 + 0.002 * (seed % 15), indel_frac=0.4, homopolymer_bias=True,
+                divergence=(0.02, 0.06))
+    sg = synth.make_subgroup(**spec)
+    b = api.StrainCallBatch()
+    b.add(sg)
+    b.thread_reads()
+    rows = [refpy.msa_align(p, "oracle") for p in b.msa_problems()]
+    with pytest.raises(api.RamblError) as e:
+        b.finish_graphs_with_rows(rows)
+    assert e.value.code == api.RAMBL_ERR_INVALID and "does not terminate" in str(e.value)
+    b.close()
