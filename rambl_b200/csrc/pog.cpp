@@ -11,8 +11,11 @@
 //     front (they only depend on the threaded reads) and solved in one device launch;
 //   * the "level without deletions" of every node (PartialOrderGraph.cpp:571-622) is taken from ONE
 //     traversal per graph, since deletion canonisation never changes the deletion-free subgraph;
-//   * reads covering an edge are counted by a sorted merge instead of the quadratic pool scan
-//     (PartialOrderGraph.cpp:1218-1244), once per edge.
+//   * reads covering an edge are counted by a sorted merge (or a binary search from the shorter pool) instead of the
+//     quadratic pool scan (PartialOrderGraph.cpp:1218-1244), once per edge;
+//   * a read pool is an ascending list of read ids wherever its entries are implied by the node (one letter, the read's
+//     copies) -- all but ~500 of the 650 000 entries of a 5 000-read subgroup -- and a list of (read, string, copies)
+//     items only where merges made it one.
 #include "pog.hpp"
 
 #include <algorithm>
