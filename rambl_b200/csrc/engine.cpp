@@ -1417,10 +1417,13 @@ std::string strain_sequence(const FlatGraph& g, const std::vector<int>& path)
 std::string strain_plain_sequence(const FlatGraph& g, const std::vector<int>& path)
 {
     std::string r;
+    r.reserve(path.size());
     for (int u : path)
     {
-        const std::string l = g.label(u);
-        if (l != "^" && l != "$" && l != "-" && l != "=") r += l;
+        const char* l = g.label_chars.data() + g.label_off[u];
+        const int n = g.label_off[u + 1] - g.label_off[u];
+        if (n == 1 && (l[0] == '^' || l[0] == '$' || l[0] == '-' || l[0] == '=')) continue;  // the four one-letter marks
+        r.append(l, (size_t)n);
     }
     return r;
 }
