@@ -159,6 +159,10 @@ int rambl_batch_infer(rambl_batch* b, int32_t n, float e, float tau, float diff,
  * second chunk while the device searches the strains of the first (two CUDA streams, two driver threads).
  * Same results as the two calls (subgroups never interact); what StrainCall's main() loop is to the CLI. */
 int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff, int32_t do_assign, int32_t keep_loglik);
+/* The chunk layout rambl_batch_solve would use for n_subgroups on a device with `sms` SMs: writes up to `cap` chunk bounds
+ * (chunk c = subgroups bounds[c] .. bounds[c+1]-1) and returns how many there are (chunks + 1), or a negative error.  Needs no
+ * device; honours $RAMBL_SOLVE_FIRST / $RAMBL_SOLVE_CHUNKS. */
+int32_t rambl_solve_layout(int32_t n_subgroups, int32_t sms, int32_t* bounds, int32_t cap);
 
 /* ---- results */
 int32_t rambl_batch_num_subgroups(const rambl_batch* b);

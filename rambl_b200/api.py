@@ -58,6 +58,7 @@ SYMBOLS = {
     "rambl_free": (None, [C.c_void_p]),
     "rambl_release_cached_memory": (None, []),
     "rambl_cached_host_bytes": (C.c_int64, []),
+    "rambl_solve_layout": (C.c_int32, [C.c_int32, C.c_int32, _i32p, C.c_int32]),
     "rambl_set_gibbs_blocks": (C.c_int, [C.c_int32]),
     "rambl_set_host_threads": (C.c_int, [C.c_int32]),
     "rambl_set_walk_mode": (C.c_int, [C.c_int32]),
@@ -143,6 +144,15 @@ def device_count() -> int:
 def release_cached_memory() -> None:
     """Cached device, pinned and pageable host blocks go back to the driver / the allocator."""
     lib().rambl_release_cached_memory()
+
+
+def solve_layout(n_subgroups: int, sms: int = 148) -> List[int]:
+    """Chunk bounds rambl_batch_solve uses for a batch of n_subgroups on a device with `sms` SMs (no device needed)."""
+    buf = np.zeros(64, dtype=np.int32)
+    n = lib().rambl_solve_layout(n_subgroups, sms, buf.ctypes.data_as(_i32p), len(buf))
+    if n < 0:
+        _check(-n)
+    return [int(x) for x in buf[:min(n, len(buf))]]
 
 
 def cached_host_bytes() -> int:

@@ -612,6 +612,45 @@ int rambl_batch_infer(rambl_batch* b, int32_t n, float e, float tau, float diff,
     });
 }
 
+// Chunk bounds of the overlapped solve for a batch of N subgroups on a device with `sms` SMs (bound[c] .. bound[c+1] is
+// chunk c).  A batch of up to one wave of the walk kernel is one chunk: it gains nothing from chunks (its chains are
+// latency-bound and get clusters instead).  Otherwise the first chunk is one wave minus a few SMs -- a walk CTA takes the
+// whole shared memory of its SM for half a second or more, and the small launches of the NEXT chunk's set-up (its
+// insertion alignment, the model initialisation) need somewhere to run before the first walk CTAs retire -- and the rest
+// follows in chunks of at most eight waves.  $RAMBL_SOLVE_CHUNKS = k: k equal chunks instead; $RAMBL_SOLVE_FIRST = n: size
+// of the first chunk (both for measurements and tests; results do not depend on the layout).
+static std::vector<size_t> solve_chunk_bounds(size_t N, int sms)
+{
+    std::vector<size_t> bound(1, 0);
+    const size_t wave = (size_t)std::max(sms, 1);
+    const char* ef = getenv("RAMBL_SOLVE_FIRST");
+    const char* ec = getenv("RAMBL_SOLVE_CHUNKS");
+    size_t first = (size_t)std::max(sms - 8, 1);
+    if (ef) first = (size_t)std::max(1, atoi(ef));
+    if (ec && atoi(ec) >= 1)
+    {
+        const size_t k = std::min<size_t>((size_t)atoi(ec), std::max<size_t>(N, 1));
+        for (size_t c = 1; c <= k; ++c) bound.push_back(N * c / k);
+    }
+    else if (N <= first || (!ef && N <= wave)) bound.push_back(N);
+    else
+    {
+        bound.push_back(first);
+        const size_t rest = N - first, cap = 8 * wave;
+        const size_t k = (rest + cap - 1) / cap;
+        for (size_t c = 1; c <= k; ++c) bound.push_back(first + rest * c / k);
+    }
+    return bound;
+}
+
+int32_t rambl_solve_layout(int32_t n_subgroups, int32_t sms, int32_t* bounds, int32_t cap)
+{
+    if (n_subgroups < 0 || sms < 1 || (cap > 0 && !bounds)) return -fail(RAMBL_ERR_INVALID, "bad layout query");
+    const std::vector<size_t> b = solve_chunk_bounds((size_t)n_subgroups, sms);
+    for (size_t i = 0; i < b.size() && (int32_t)i < cap; ++i) bounds[i] = (int32_t)b[i];
+    return (int32_t)b.size();
+}
+
 // rambl_batch_build_graphs + rambl_batch_infer as ONE call that overlaps them.  The subgroups are dealt into chunks --
 // the first is one wave of the walk kernel (one subgroup per SM), so that the device starts as early as possible; the rest
 // follows in one chunk (several for very large batches) -- and two driver threads, each with its own CUDA stream, take the
@@ -630,32 +669,9 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
         int device = 0, sms = 148;
         RAMBL_CUDA(cudaGetDevice(&device));
         RAMBL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        // chunk bounds.  A batch of up to one wave gains nothing from chunks (its chains are latency-bound and get
-        // clusters instead).  $RAMBL_SOLVE_CHUNKS = k: k equal chunks; $RAMBL_SOLVE_FIRST = n: size of the first chunk.
-        std::vector<size_t> bound(1, 0);
+        const std::vector<size_t> bound = solve_chunk_bounds(N, sms);
         size_t n_drivers = 2;
-        {
-            // one wave minus a few SMs: a walk CTA takes the whole shared memory of its SM for half a second or more, and
-            // the small launches of the NEXT chunk's set-up (its insertion alignment, the model initialisation) need
-            // somewhere to run before the first walk CTAs retire
-            size_t first = (size_t)std::max(sms - 8, 1);
-            if (const char* ev = getenv("RAMBL_SOLVE_FIRST")) first = (size_t)std::max(1, atoi(ev));
-            const char* ev = getenv("RAMBL_SOLVE_CHUNKS");
-            if (ev && atoi(ev) >= 1)
-            {
-                const size_t k = std::min<size_t>((size_t)atoi(ev), std::max<size_t>(N, 1));
-                for (size_t c = 1; c <= k; ++c) bound.push_back(N * c / k);
-            }
-            else if (N <= first || (!getenv("RAMBL_SOLVE_FIRST") && N <= (size_t)std::max(sms, 1))) bound.push_back(N);
-            else
-            {
-                bound.push_back(first);
-                const size_t rest = N - first, cap = 8 * (size_t)std::max(sms, 1);
-                const size_t k = (rest + cap - 1) / cap;
-                for (size_t c = 1; c <= k; ++c) bound.push_back(first + rest * c / k);
-            }
-            if (const char* ev2 = getenv("RAMBL_SOLVE_DRIVERS")) n_drivers = (size_t)std::max(1, atoi(ev2));
-        }
+        if (const char* ev = getenv("RAMBL_SOLVE_DRIVERS")) n_drivers = (size_t)std::max(1, atoi(ev));
         const size_t n_chunks = bound.size() - 1;
         n_drivers = std::min(n_drivers, std::max<size_t>(n_chunks, 1));
         if (!fresh || n_chunks <= 1)

@@ -317,3 +317,31 @@ def test_input_on_which_the_reference_never_ends_is_refused():
         b.finish_graphs_with_rows(rows)
     assert e.value.code == api.RAMBL_ERR_INVALID and "does not terminate" in str(e.value)
     b.close()
+
+
+def test_chunk_layout_of_the_overlapped_solve(monkeypatch):
+    """rambl_solve_layout (no device): up to one wave of the walk kernel is one chunk; a larger batch starts with one wave
+    minus 8 SMs and continues in chunks of at most eight waves; the two environment overrides; the bounds always start at
+    0, end at N and do not decrease."""
+    for k in ("RAMBL_SOLVE_FIRST", "RAMBL_SOLVE_CHUNKS"):
+        monkeypatch.delenv(k, raising=False)
+    assert api.solve_layout(0) == [0, 0]
+    assert api.solve_layout(62) == [0, 62]
+    assert api.solve_layout(148) == [0, 148]
+    assert api.solve_layout(149) == [0, 140, 149]
+    assert api.solve_layout(250) == [0, 140, 250]
+    assert api.solve_layout(500) == [0, 140, 500]
+    assert api.solve_layout(140 + 8 * 148) == [0, 140, 140 + 8 * 148]
+    big = api.solve_layout(5000)
+    assert big[:2] == [0, 140] and big[-1] == 5000 and len(big) == 2 + 5  # 4860 subgroups in five chunks of <= 1184
+    assert all(b - a <= 8 * 148 for a, b in zip(big[1:], big[2:])) and big == sorted(big)
+    assert api.solve_layout(500, sms=132) == [0, 124, 500]
+    monkeypatch.setenv("RAMBL_SOLVE_FIRST", "7")
+    assert api.solve_layout(24) == [0, 7, 24]
+    assert api.solve_layout(5) == [0, 5]
+    monkeypatch.delenv("RAMBL_SOLVE_FIRST")
+    monkeypatch.setenv("RAMBL_SOLVE_CHUNKS", "3")
+    assert api.solve_layout(24) == [0, 8, 16, 24]
+    assert api.solve_layout(2) == [0, 1, 2]
+    with pytest.raises(api.RamblError):
+        api.solve_layout(-1)
