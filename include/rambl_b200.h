@@ -164,6 +164,12 @@ int rambl_batch_solve(rambl_batch* b, int32_t n, float e, float tau, float diff,
  * device; honours $RAMBL_SOLVE_FIRST / $RAMBL_SOLVE_CHUNKS. */
 int32_t rambl_solve_layout(int32_t n_subgroups, int32_t sms, int32_t* bounds, int32_t cap);
 
+/* What the device-resident walk will do with subgroup sg (graphs must be built; needs no device -- the level tables are a
+ * property of the graph): out = { eligible, stops at an early "$" and hands over to the level-synchronous path, reason when not
+ * eligible (engine.hpp), graph levels, read-pool entries over all levels, most entries of one level, most draws of one level,
+ * levels on which a one-letter strain label can meet a multi-letter read string (deviation (i)) }. */
+int rambl_batch_walk_plan(const rambl_batch* b, int32_t sg, int64_t out[8]);
+
 /* ---- results */
 int32_t rambl_batch_num_subgroups(const rambl_batch* b);
 int32_t rambl_batch_num_nodes(const rambl_batch* b, int32_t sg);

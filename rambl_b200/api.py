@@ -59,6 +59,7 @@ SYMBOLS = {
     "rambl_release_cached_memory": (None, []),
     "rambl_cached_host_bytes": (C.c_int64, []),
     "rambl_solve_layout": (C.c_int32, [C.c_int32, C.c_int32, _i32p, C.c_int32]),
+    "rambl_batch_walk_plan": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
     "rambl_set_gibbs_blocks": (C.c_int, [C.c_int32]),
     "rambl_set_host_threads": (C.c_int, [C.c_int32]),
     "rambl_set_walk_mode": (C.c_int, [C.c_int32]),
@@ -305,6 +306,15 @@ class StrainCallBatch:
         pk = sg.packed()
         return self.add_subgroup_packed(sg.gene, pk["pos"], pk["cigar_off"], pk["cigar_chars"], pk["seq_off"], pk["seq_chars"],
                                         pk["cn"], sg.pair_off, sg.pair_val)
+
+    def walk_plan(self, sg: int) -> dict:
+        """What the device-resident walk will do with subgroup sg (no device needed once the graph is built)."""
+        out = (C.c_int64 * 8)()
+        _check(lib().rambl_batch_walk_plan(self._h, sg, out))
+        keys = ("eligible", "handoff", "reason", "levels", "entries", "max_entries", "max_draws", "offtable_levels")
+        d = {k: int(v) for k, v in zip(keys, out)}
+        d["eligible"], d["handoff"] = bool(d["eligible"]), bool(d["handoff"])
+        return d
 
     def build_graphs(self):
         _check(lib().rambl_batch_build_graphs(self._h))

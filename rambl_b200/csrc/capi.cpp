@@ -901,6 +901,18 @@ char* rambl_batch_fasta(const rambl_batch* b, int32_t sg, const char* gene_name,
     catch (const Error& e) { fail(e.code, e.what()); return nullptr; }
 }
 
+int rambl_batch_walk_plan(const rambl_batch* b, int32_t sg, int64_t out[8])
+{
+    return guarded([&] {
+        if (!out) throw Error(RAMBL_ERR_INVALID, "null argument");
+        const Subgroup* s = sub_at(b, sg);
+        if (!s->built) throw Error(RAMBL_ERR_STATE, "graphs are not built");
+        const WalkEligibility w = walk_eligibility(s->graph, s->input);
+        out[0] = w.eligible; out[1] = w.handoff; out[2] = w.reason; out[3] = w.levels;
+        out[4] = w.entries; out[5] = w.max_entries; out[6] = w.max_draws; out[7] = w.offtable_levels;
+    });
+}
+
 int rambl_batch_stats(const rambl_batch* b, rambl_stats* out)
 {
     if (!b || !out) return fail(RAMBL_ERR_INVALID, "null argument");

@@ -915,11 +915,11 @@ struct Engine
     // simply has its pool listed on both (as prepare() does), a read with several entries on one level has the later
     // ones flagged (they are added after the first, in entry order).  Anything else goes through the
     // level-synchronous path.
-    void plan_walk(size_t i)
+    void plan_walk(size_t i) { plan_walk_graph(*subs[i].g, *subs[i].in, subs[i].R, plans[i]); }
+
+    // (a function of the graph and the read pairs alone: walk_eligibility() below answers without a device)
+    static void plan_walk_graph(const FlatGraph& g, const SubgroupInput& in, int R, WalkPlan& p)
     {
-        const Sub& s = subs[i];
-        WalkPlan& p = plans[i];
-        const FlatGraph& g = *s.g;
         p = WalkPlan();
         if (g.n_nodes < 2 || g.end_node < 0) { p.reason = 8; return; }
         std::vector<int> mark(g.n_nodes, -1);
@@ -984,8 +984,7 @@ struct Engine
             level += 1;
         }
         if (!ok || !ended || level < 2) { if (!p.reason) p.reason = 2; return; }
-        const SubgroupInput& in = *s.in;
-        for (int v : in.pair_val) if (v >= s.R) { p.reason = 7; return; }  // reported by the level-synchronous path
+        for (int v : in.pair_val) if (v >= R) { p.reason = 7; return; }  // reported by the level-synchronous path
         p.n_levels = level;
         p.eligible = true;
     }
@@ -1398,6 +1397,22 @@ struct Engine
 };
 
 }  // namespace
+
+WalkEligibility walk_eligibility(const FlatGraph& g, const SubgroupInput& in)
+{
+    Engine::WalkPlan p;
+    Engine::plan_walk_graph(g, in, std::max(1, g.n_reads), p);
+    WalkEligibility e;
+    e.eligible = p.eligible;
+    e.handoff = p.handoff;
+    e.reason = p.reason;
+    e.levels = p.eligible ? p.n_levels : (int)p.lvl_ent_off.size() - 1;
+    e.entries = p.n_ent;
+    e.max_entries = p.max_m;
+    e.max_draws = p.max_D;
+    e.offtable_levels = p.mixed_levels;
+    return e;
+}
 
 static int g_walk_mode = 1, g_walk_blocks = 0, g_walk_cluster = 0;
 void set_walk_cluster(int c) { g_walk_cluster = c; }

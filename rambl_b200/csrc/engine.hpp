@@ -88,6 +88,21 @@ int walk_blocks();
 void set_walk_cluster(int c);
 int walk_cluster();
 
+// What the device-resident walk would do with a subgroup -- a function of the graph and the read pairs alone (the
+// level tables are a property of the graph), so it needs no device.
+struct WalkEligibility
+{
+    bool eligible = false;   // the walk takes the subgroup
+    bool handoff = false;    // ... up to an early "$" (a level that holds "$" next to other nodes); the level-synchronous path finishes it
+    int reason = 0;          // why not: 1 not a DAG, 2 something follows "$" / "$" not reached, 4 entry range (copies or letters > 255),
+                             // 5 "^" carries reads, 6 size, 7 mate id out of range, 8 no graph
+    int levels = 0;          // graph levels the walk runs (planned so far when not eligible)
+    long long entries = 0;   // read-pool entries over all levels (an entry counts once per level its node is listed on)
+    int max_entries = 0, max_draws = 0;  // of one level
+    int offtable_levels = 0; // levels with a multi-letter read string next to a one-letter node
+};
+WalkEligibility walk_eligibility(const FlatGraph& g, const SubgroupInput& in);
+
 void infer_batch(const std::vector<SubgroupInput>& in, const InferParams& prm, std::vector<SubgroupResult>& out,
                  EngineStats& stats, cudaStream_t stream = 0);
 

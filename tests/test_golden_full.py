@@ -64,4 +64,28 @@ def test_host_graph_construction_at_full_size_equals_the_reference(name):
     assert b.num_nodes(0) == case["n_nodes"]
     assert hashlib.sha256(strip_sib(b.graph_dump(0)).encode()).hexdigest() == case["dump_nosib_sha256"]
     assert hashlib.sha256(b.output_edge(0).encode()).hexdigest() == case["edges_sha256"]
+    # what the device walk will do with it is a property of the graph: every fixture goes to the walk kernel as a whole, and
+    # none has a level on which a one-letter strain label could meet a multi-letter read string (deviation (i))
+    plan = b.walk_plan(0)
+    assert plan["eligible"] and not plan["handoff"] and plan["reason"] == 0 and plan["offtable_levels"] == 0, plan
+    assert plan["levels"] > 100 and 0 < plan["max_draws"] <= 40000 * 8  # (collapsed paths shorten the walk, insertion columns lengthen it)
     b.close()
+
+
+def test_subgroup_whose_graph_is_not_strictly_levelled_is_handed_over_at_the_early_end():
+    """configs[2] subgroup 383: "$" shares a level with other nodes, every node sits on two levels (twice the read-pool entries
+    of its neighbours -- why its chain is the longest of the workload); the walk takes it up to that level."""
+    from oracle import refpy
+    from rambl_b200 import api
+    plans = {}
+    for k in (382, 383):
+        sg = synth.config2_subgroup(k)
+        b = api.StrainCallBatch()
+        b.add(sg)
+        b.thread_reads()
+        b.finish_graphs_with_rows([refpy.msa_align(p, "oracle") for p in b.msa_problems()])
+        plans[k] = b.walk_plan(0)
+        b.close()
+    assert plans[382]["eligible"] and not plans[382]["handoff"]
+    assert plans[383]["eligible"] and plans[383]["handoff"] and plans[383]["offtable_levels"] == 0
+    assert plans[383]["entries"] > 1.8 * plans[382]["entries"]
