@@ -132,6 +132,7 @@ HostCache& host_cache()
 void* cached_host_alloc(size_t bytes)
 {
     if (bytes == 0) bytes = 1;
+    if (bytes > (size_t)-1 - 0x20000) throw std::bad_alloc();  // the rounding below must not wrap
     size_t cap = bytes;
     void* base = nullptr;
     if (bytes >= kHostSmall)
@@ -151,7 +152,6 @@ void* cached_host_alloc(size_t bytes)
     }
     if (!base)
     {
-        if (cap > (size_t)-1 - kHostHeader) throw std::bad_alloc();
         base = malloc(kHostHeader + cap);
         if (!base) throw std::bad_alloc();
     }
